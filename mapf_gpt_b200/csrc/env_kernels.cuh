@@ -1,0 +1,438 @@
+// env_kernels.cuh -- integer/byte kernels of the rollout path (HBM-bound, no tensor cores):
+//   bfs_kernel         cost-to-go field per (env, agent)   observation_generator.cpp:134-176,200-220
+//   set_state_kernel   positions/goals/actions from host   observation_generator.cpp:432-478
+//   observe_kernel     history + greedy bits + tokenizer   observation_generator.cpp:412-430,288-311,487-528,352-389
+//   sample_step_kernel GPT.act sampling (model.py:249-259) + POGEMA `soft` step
+//
+// HBM layout (capacity E envs x N agents, H x W grid, row pitch P = roundup(W, 8)):
+//   obst  u8  [E][H][P]      loc  i16 [E][H][P] (agent id or -1)     c2g u16 [E][N][H][P]
+//   pos, goal  short2 [E][N] (x = row, y = col)                       hist u8 [E][N][8] (5 used)
+//   nextb u8 [E][N]          act i32 [E][N]                           tokens u8 [E*N][256]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mg {
+
+struct EnvState {
+    int E, N, H, W, P;
+    uint8_t *obst;
+    int16_t *loc;
+    uint16_t *c2g;
+    short2 *pos, *goal;
+    uint8_t *hist;
+    uint8_t *nextb;
+    int32_t *act;
+    int32_t *nag;        // agents per env (0 = slot unused)
+    uint8_t *dirty;      // [E][N] cost-to-go must be recomputed
+    uint8_t *tokens;
+    float *logits;       // [E*N][8]
+    // episode bookkeeping
+    int32_t *steps;      // [E]
+    uint8_t *done;       // [E]
+    int32_t *arrive;     // [E][N] step at which the agent last arrived on its goal, -1 = not on goal
+    unsigned long long *agent_steps;  // [E]
+    int32_t *vocab_err;  // [1]
+};
+
+__constant__ int c_moves[5][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+
+// ------------------------------------------------------------------------------------------------
+// Level-synchronous BFS from the goal over the whole padded grid, one block per (env, agent).
+// For H,W <= 74 this IS compute_cost2go_partial: window = grid, only seed = goal.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bfs_kernel(EnvState s, int first_env, int only_dirty)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int cells = s.H * s.P;
+    uint16_t *dist = reinterpret_cast<uint16_t *>(sm);
+    uint16_t *q0 = dist + cells;
+    uint16_t *q1 = q0 + cells;
+    uint8_t *ob = reinterpret_cast<uint8_t *>(q1 + cells);
+    __shared__ int n_next;
+
+    const int e = first_env + blockIdx.x / s.N, a = blockIdx.x % s.N;
+    if (a >= s.nag[e]) return;
+    if (only_dirty && !s.dirty[e * s.N + a]) return;
+    const uint8_t *og = s.obst + (size_t)e * cells;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        dist[i] = 0xFFFF;
+        ob[i] = (i % s.P) < s.W ? og[i] : 1;
+    }
+    const short2 g = s.goal[e * s.N + a];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dist[g.x * s.P + g.y] = 0;
+        q0[0] = (uint16_t)(g.x * s.P + g.y);
+        n_next = 0;
+    }
+    __syncthreads();
+    int n_cur = 1, level = 0;
+    uint16_t *qc = q0, *qn = q1;
+    while (n_cur > 0) {
+        for (int i = threadIdx.x; i < n_cur; i += blockDim.x) {
+            const int c = qc[i];
+            const int ci = c / s.P, cj = c - ci * s.P;
+#pragma unroll
+            for (int m = 1; m < 5; m++) {
+                const int ni = ci + c_moves[m][0], nj = cj + c_moves[m][1];
+                if (ni < 0 || nj < 0 || ni >= s.H || nj >= s.W) continue;
+                const int nc = ni * s.P + nj;
+                if (ob[nc]) continue;
+                if (atomicCAS(reinterpret_cast<unsigned short *>(&dist[nc]), (unsigned short)0xFFFF,
+                              (unsigned short)(level + 1)) == 0xFFFF)
+                    qn[atomicAdd(&n_next, 1)] = (uint16_t)nc;
+            }
+        }
+        __syncthreads();
+        n_cur = n_next;
+        __syncthreads();
+        if (threadIdx.x == 0) n_next = 0;
+        uint16_t *t = qc; qc = qn; qn = t;
+        level++;
+        __syncthreads();
+    }
+    uint16_t *out = s.c2g + ((size_t)e * s.N + a) * cells;
+    for (int i = threadIdx.x; i < cells / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<uint32_t *>(dist)[i];
+    if (threadIdx.x == 0) s.dirty[e * s.N + a] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// update_agents, first half (cpp:432-478): take positions / goals / actions from staging buffers.
+// One block per env.  loc is cleared for ALL old cells before any new cell is written (cpp:434-435).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) set_state_kernel(EnvState s, const int32_t *__restrict__ pos_in,
+                                                        const int32_t *__restrict__ goal_in,
+                                                        const int32_t *__restrict__ act_in)
+{
+    const int e = blockIdx.x;
+    const int n = s.nag[e];
+    if (n == 0) return;
+    const int cells = s.H * s.P;
+    int16_t *loc = s.loc + (size_t)e * cells;
+    if (pos_in) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const short2 p = s.pos[e * s.N + i];
+            loc[p.x * s.P + p.y] = -1;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int x = pos_in[(e * s.N + i) * 2], y = pos_in[(e * s.N + i) * 2 + 1];
+            s.pos[e * s.N + i] = make_short2((short)x, (short)y);
+        }
+        __syncthreads();
+        // agents_locations[pos] = i in index order: on a (never legal) shared cell the highest id wins
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const short2 p = s.pos[e * s.N + i];
+            loc[p.x * s.P + p.y] = (int16_t)i;
+        }
+    }
+    if (goal_in) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int x = goal_in[(e * s.N + i) * 2], y = goal_in[(e * s.N + i) * 2 + 1];
+            const short2 g = s.goal[e * s.N + i];
+            if (g.x != x || g.y != y) {
+                s.goal[e * s.N + i] = make_short2((short)x, (short)y);
+                s.dirty[e * s.N + i] = 1;
+            }
+        }
+    }
+    if (act_in) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s.act[e * s.N + i] = act_in[e * s.N + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// observe_kernel: one block per env.
+//   phase A (kUpdate): history push (cpp:441-462) + greedy-direction bits (update_next_action, cpp:412-430)
+//   phase B (kTokens): cost-to-go window (cpp:288-311), 13 nearest agents by (manhattan, id)
+//                      (cpp:487-514), Encoder::encode (cpp:352-389) -> 256 uint8 tokens per agent.
+// Trained shape only: radius 5, 13 agents, 5 previous actions, limit 20, context 256.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int field_dist(const uint16_t *F, int x, int y, int H, int W, int P)
+{   // get_distance, cpp:313-319: window = [0,H-1] x [0,W-1], upper bounds EXCLUSIVE
+    if (x < 0 || x >= H - 1 || y < 0 || y >= W - 1) return -1;
+    return F[x * P + y];
+}
+
+template <bool kUpdate, bool kTokens>
+__global__ void __launch_bounds__(256) observe_kernel(EnvState s)
+{
+    const int e = blockIdx.x;
+    const int n = s.nag[e];
+    if (n == 0) return;
+    const int cells = s.H * s.P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint8_t tokbuf[8][256];
+    __shared__ int sel[8][16];
+
+    if (kUpdate) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int idx = e * s.N + i;
+            const int a = s.act[idx];
+            uint8_t *h = s.hist + (size_t)idx * 8;
+            h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = h[4];
+            h[4] = (a >= 0 && a <= 4) ? (uint8_t)(45 + a) : (uint8_t)44;
+            const uint16_t *F = s.c2g + (size_t)idx * cells;
+            const short2 p = s.pos[idx];
+            const int cur = field_dist(F, p.x, p.y, s.H, s.W, s.P);
+            int bits = 0;
+#pragma unroll
+            for (int m = 1; m < 5; m++) {
+                const int nb = field_dist(F, p.x + c_moves[m][0], p.y + c_moves[m][1], s.H, s.W, s.P);
+                bits = (bits << 1) | ((nb >= 0 && cur > nb) ? 1 : 0);
+            }
+            s.nextb[idx] = (uint8_t)bits;
+        }
+        __syncthreads();
+    }
+    if (!kTokens) return;
+
+    const int16_t *loc = s.loc + (size_t)e * cells;
+    for (int i = warp; i < n; i += (blockDim.x >> 5)) {
+        const int idx = e * s.N + i;
+        const uint16_t *F = s.c2g + (size_t)idx * cells;
+        const short2 p = s.pos[idx];
+        const int mid = F[p.x * s.P + p.y];
+        uint8_t *tb = tokbuf[warp];
+        unsigned key[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int w = lane + 32 * t;
+            key[t] = 0xFFFFFFFFu;
+            if (w < 121) {
+                const int wi = w / 11, wj = w - wi * 11;
+                const int c = (p.x - 5 + wi) * s.P + (p.y - 5 + wj);
+                const int v = F[c];
+                int tok;
+                if (v == 0xFFFF) tok = 41;
+                else {
+                    const int d = v - mid;
+                    tok = d > 20 ? 43 : (d < -20 ? 42 : d + 20);
+                }
+                tb[w] = (uint8_t)tok;
+                const int id = loc[c];
+                if (id >= 0) key[t] = ((unsigned)(abs(wi - 5) + abs(wj - 5)) << 16) | (unsigned)id;
+            }
+        }
+        // 13 smallest keys (distance, then agent id), warp-wide
+        int count = 0;
+#pragma unroll 1
+        for (int k = 0; k < 13; k++) {
+            const unsigned lm = min(min(key[0], key[1]), min(key[2], key[3]));
+            const unsigned m = __reduce_min_sync(0xffffffffu, lm);
+            if (m == 0xFFFFFFFFu) break;
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (key[t] == m) key[t] = 0xFFFFFFFFu;
+            if (lane == 0) sel[warp][k] = (int)(m & 0xFFFF);
+            count++;
+        }
+        __syncwarp();
+        for (int t = lane; t < 135; t += 32) {  // 130 slot tokens + 5 tail pads
+            uint8_t tok = 66;
+            const int slot = t / 10, f = t - slot * 10;
+            if (slot < count) {
+                const int j = e * s.N + sel[warp][slot];
+                if (f < 4) {
+                    const short2 q = (f < 2) ? s.pos[j] : s.goal[j];
+                    int d = ((f & 1) ? q.y - p.y : q.x - p.x);
+                    if (f >= 2) d = max(-20, min(20, d));               // relative goal is clamped (cpp:360-361)
+                    else if (d < -20 || d > 20) atomicExch(s.vocab_err, 1);  // int_vocab.at() would throw
+                    tok = (uint8_t)(d + 20);
+                } else if (f < 9) tok = s.hist[(size_t)j * 8 + (f - 4)];
+                else tok = (uint8_t)(50 + s.nextb[j]);
+            }
+            tb[121 + t] = tok;
+        }
+        __syncwarp();
+        reinterpret_cast<uint2 *>(s.tokens + (size_t)idx * 256)[lane] = reinterpret_cast<const uint2 *>(tb)[lane];
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based; one independent stream per (seed, env, agent, step))
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float exp1_from_bits(uint32_t b)
+{   // u in (0,1], q = -log(u) ~ Exp(1)   (torch.multinomial draws q with exponential_(1))
+    const float u = ((float)(b >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    return -logf(u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample_step_kernel: one block per env.
+//   (1) GPT.act tail (model.py:249-259): softmax over logits[0:5]; greedy argmax, or
+//       multinomial == argmax(p / q), q ~ Exp(1) from Philox (mode 1) or supplied (mode 2).
+//   (2) POGEMA soft step (App. C.3) in its order-independent fixed-point form:
+//       W = waits  U obstacle targets  U swaps  U (movers into one cell, all but the lowest index)
+//           U followers of an occupant in W (iterated);   everyone outside W moves at once.
+//   (3) episode counters (App. C.4-C.5).
+// mode: 0 greedy, 1 philox, 2 supplied q, 3 = actions already in s.act (host supplied).
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+    int mode;
+    int do_step;
+    const float *q;          // mode 2: [E*N][5]
+    unsigned long long seed;
+    const int32_t *act_override;  // actions to EXECUTE (history keeps s.act = the sampled ones), or null
+    int env_offset;          // global env id of slot 0 (multi-GPU sharding: streams follow the env, not the rank)
+    int max_episode_steps;   // 0 = unlimited
+};
+
+__global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int e = blockIdx.x;
+    const int n = s.nag[e];
+    if (n == 0) return;
+    const int cells = s.H * s.P;
+    int *claim = reinterpret_cast<int *>(sm);                 // [cells]
+    int *tgt = claim + cells;                                 // [N]
+    uint8_t *wait = reinterpret_cast<uint8_t *>(tgt + s.N);   // [N]
+    int16_t *loc = s.loc + (size_t)e * cells;
+    const uint8_t *ob = s.obst + (size_t)e * cells;
+    const int t_now = s.steps[e];
+    const bool frozen = s.done[e] != 0;
+
+    if (a.mode != 3) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int idx = e * s.N + i;
+            const float *l = s.logits + (size_t)idx * 8;
+            const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3], l4 = l[4];
+            const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
+            float p[5] = {expf(l0 - mx), expf(l1 - mx), expf(l2 - mx), expf(l3 - mx), expf(l4 - mx)};
+            const float sum = (((p[0] + p[1]) + p[2]) + p[3]) + p[4];
+            float q[5] = {1.f, 1.f, 1.f, 1.f, 1.f};
+            if (a.mode == 1) {
+                uint32_t r0[4], r1[4];
+                const uint32_t ge = (uint32_t)(a.env_offset + e);
+                philox4x32_10(ge, (uint32_t)i, (uint32_t)t_now, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r0);
+                philox4x32_10(ge, (uint32_t)i, (uint32_t)t_now, 1u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r1);
+                q[0] = exp1_from_bits(r0[0]); q[1] = exp1_from_bits(r0[1]); q[2] = exp1_from_bits(r0[2]);
+                q[3] = exp1_from_bits(r0[3]); q[4] = exp1_from_bits(r1[0]);
+            } else if (a.mode == 2) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) q[k] = a.q[(size_t)idx * 5 + k];
+            }
+            int best = 0;
+            float bv = (p[0] / sum) / q[0];
+#pragma unroll
+            for (int k = 1; k < 5; k++) {
+                const float v = (p[k] / sum) / q[k];
+                if (v > bv) { bv = v; best = k; }
+            }
+            s.act[idx] = best;
+        }
+    }
+    if (!a.do_step || frozen) return;
+    __syncthreads();
+
+    // ---- soft collision step
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) claim[i] = 0x7FFFFFFF;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int idx = e * s.N + i;
+        int act = a.act_override ? a.act_override[idx] : s.act[idx];
+        if (act < 0 || act > 4) act = 0;
+        const short2 p = s.pos[idx];
+        const int t = (p.x + c_moves[act][0]) * s.P + (p.y + c_moves[act][1]);
+        tgt[i] = t;
+        wait[i] = (act == 0 || ob[t] != 0) ? 1 : 0;       // (a) waits and obstacle targets
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {   // (b) swaps
+        if (wait[i]) continue;
+        const int j = loc[tgt[i]];
+        const short2 p = s.pos[e * s.N + i];
+        if (j >= 0 && j != i && tgt[j] == p.x * s.P + p.y) wait[i] = 2;  // mark; applied after the sweep
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (wait[i] == 2) wait[i] = 1;
+        if (!wait[i]) atomicMin(&claim[tgt[i]], i);        // (c) lowest-index mover keeps the claim
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (!wait[i] && claim[tgt[i]] != i) wait[i] = 1;
+    // (d) followers of a blocked occupant, to the fixed point
+    while (true) {
+        __syncthreads();
+        int changed = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (wait[i]) continue;
+            const int k = loc[tgt[i]];
+            if (k >= 0 && wait[k]) { wait[i] = 1; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // apply all surviving moves at once
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (!wait[i]) {
+            const short2 p = s.pos[e * s.N + i];
+            loc[p.x * s.P + p.y] = -1;
+        }
+    __syncthreads();
+    int on_goal = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int idx = e * s.N + i;
+        short2 p = s.pos[idx];
+        if (!wait[i]) {
+            const int t = tgt[i];
+            p = make_short2((short)(t / s.P), (short)(t % s.P));
+            s.pos[idx] = p;
+            loc[t] = (int16_t)i;
+        }
+        const short2 g = s.goal[idx];
+        const bool og = (p.x == g.x && p.y == g.y);
+        if (og) { if (s.arrive[idx] < 0) s.arrive[idx] = t_now + 1; }
+        else s.arrive[idx] = -1;
+        on_goal += og ? 1 : 0;
+    }
+    __shared__ int s_on;
+    if (threadIdx.x == 0) s_on = 0;
+    __syncthreads();
+    if (on_goal) atomicAdd(&s_on, on_goal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.steps[e] = t_now + 1;
+        s.agent_steps[e] += (unsigned long long)n;
+        if (s_on == n || (a.max_episode_steps > 0 && t_now + 1 >= a.max_episode_steps)) s.done[e] = 1;
+    }
+}
+
+// per-slot metrics (App. C.5): [ep_length, CSR, ISR, SoC, makespan, on_goal_now, agent_steps, n_agents]
+__global__ void metrics_kernel(EnvState s, double *out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= s.E) return;
+    const int n = s.nag[e];
+    double *o = out + (size_t)e * 8;
+    if (n == 0) { for (int k = 0; k < 8; k++) o[k] = 0.0; return; }
+    const int T = s.steps[e];
+    int on = 0, soc = 0, mk = 0;
+    for (int i = 0; i < n; i++) {
+        const int a = s.arrive[e * s.N + i];
+        const int cost = a >= 0 ? a : T;
+        on += a >= 0 ? 1 : 0;
+        soc += cost;
+        mk = max(mk, cost);
+    }
+    o[0] = T; o[1] = on == n ? 1.0 : 0.0; o[2] = (double)on / n; o[3] = soc; o[4] = mk; o[5] = on;
+    o[6] = (double)s.agent_steps[e]; o[7] = n;
+}
+
+}  // namespace mg
