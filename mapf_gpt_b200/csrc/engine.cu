@@ -213,7 +213,7 @@ static int ensure_workspace(mg_engine *e, int want_seqs)
     int chunk = std::min(want_seqs, 8192);
     if (chunk <= w.chunk_seqs) return MG_OK;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID);
-    w = Workspace{};
+    w.X = nullptr; w.XN = w.QKV = w.ATT = w.HID = nullptr; w.chunk_seqs = 0;
     const size_t M = (size_t)chunk * 256;
     CU(dalloc(&w.X, M * C));
     CU(dalloc(&w.XN, M * C));
