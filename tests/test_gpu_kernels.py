@@ -1,0 +1,197 @@
+"""GPU: each sm_100a kernel against its checker, through the C ABI."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD_OBS = np.load(Path(__file__).parent / "golden" / "obs_golden.npz")
+GOLD_GPT = np.load(Path(__file__).parent / "golden" / "gpt_golden.npz")
+N_SCEN = len([k for k in GOLD_OBS.files if k.endswith("_tokens")])
+LOGIT_TOL = 5e-2   # bf16 operands, fp32 accumulate/residual vs the reference's fp32 (DESIGN.md "Tolerance")
+
+
+@pytest.fixture(scope="module")
+def dev(built):
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("cfg,M,N,K", [(0, 256, 160, 160), (0, 384, 480, 160), (0, 128, 160, 640), (1, 256, 768, 256),
+                                       (1, 128, 256, 1024), (1, 256, 2304, 768), (2, 256, 384, 192), (0, 128 * 151, 640, 160)])
+def test_tcgen05_gemm(dev, cfg, M, N, K):
+    from mapf_gpt_b200 import engine as E
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device=dev, generator=g) * 0.5).bfloat16()
+    C = E.test_gemm(A, B, cfg)
+    ref = A.double() @ B.double().t()
+    assert float((C.double() - ref).abs().max()) < 1e-3 * float(ref.abs().max()) + 1e-4   # fp32 accumulation order only
+
+
+@pytest.mark.parametrize("hs,n_seq,n_head,scale", [(32, 2, 5, 1.0), (32, 3, 8, 0.2), (64, 2, 12, 1.0), (32, 1, 1, 3.0)])
+def test_tcgen05_attention(dev, hs, n_seq, n_head, scale):
+    from mapf_gpt_b200 import engine as E
+    g = torch.Generator(device=dev).manual_seed(hs + n_head)
+    q = (torch.randn(n_seq, n_head, 256, hs, device=dev, generator=g) * scale).bfloat16()
+    k = (torch.randn(n_seq, n_head, 256, hs, device=dev, generator=g) * scale).bfloat16()
+    v = torch.randn(n_seq, n_head, 256, hs, device=dev, generator=g).bfloat16()
+    o = E.test_attention(q, k, v)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())   # non-causal, model.py:58-60
+    assert float((o.float() - ref).abs().max()) < 2e-2      # P and O are rounded to bf16
+
+
+@pytest.mark.parametrize("k", range(N_SCEN))
+def test_engine_verbs_vs_golden_tokens(dev, k):
+    """update_agents + generate_observations (and the reset-time BFS) against tokens from the compiled reference."""
+    import oracle
+    from mapf_gpt_b200 import engine as E
+    grid, goals = GOLD_OBS[f"s{k}_grid"], GOLD_OBS[f"s{k}_goals"]
+    pos, act, tok = GOLD_OBS[f"s{k}_pos"], GOLD_OBS[f"s{k}_act"], GOLD_OBS[f"s{k}_tokens"]
+    n = pos.shape[1]
+    eng = E.RolloutEngine(2, n, *grid.shape)
+    eng.reset(0, grid, np.stack([pos[0], pos[0]]), np.stack([goals, goals]))
+    o = oracle.ObsOracle(grid)
+    o.create_agents(pos[0], goals)
+    for a in range(0, n, max(1, n // 5)):                                  # BFS field, bit-exact
+        assert (eng.cost2go(1, a) == o.partial(a)[1]).all()
+    for t in range(len(pos)):
+        eng.update_agents(np.stack([pos[t]] * 2), None, np.stack([act[t]] * 2))
+        got = eng.generate_observations()
+        assert (got[0] == tok[t]).all() and (got[1] == tok[t]).all(), f"scenario {k} step {t}"
+    eng.close()
+
+
+@pytest.mark.parametrize("k", [0, 4])
+def test_single_env_c_abi_twin_of_pybind_module(dev, k, built):
+    """mg_gen_* == ObservationGenerator verbs (observation_generator.cpp:548-563)."""
+    import ctypes as C
+    grid, goals = GOLD_OBS[f"s{k}_grid"], GOLD_OBS[f"s{k}_goals"]
+    pos, act, tok = GOLD_OBS[f"s{k}_pos"], GOLD_OBS[f"s{k}_act"], GOLD_OBS[f"s{k}_tokens"]
+    n = pos.shape[1]
+    g32 = np.ascontiguousarray(grid, np.int32)
+    p = lambda a: np.ascontiguousarray(a, np.int32).ctypes.data_as(C.c_void_p)
+    h = built.mg_gen_create(p(g32), grid.shape[0], grid.shape[1], None)
+    assert h
+    gl = np.ascontiguousarray(goals, np.int32)
+    assert built.mg_gen_create_agents(h, p(pos[0]), p(gl), n) == 0
+    out = np.empty((n, 256), np.int32)
+    for t in range(len(pos)):
+        assert built.mg_gen_update_agents(h, p(pos[t]), p(gl), p(act[t]), n) == 0
+        assert built.mg_gen_generate_observations(h, out.ctypes.data_as(C.c_void_p)) == 0
+        assert (out == tok[t]).all()
+    built.mg_gen_destroy(h)
+
+
+def test_goal_change_recomputes_field(dev):
+    import oracle
+    from mapf_gpt_b200 import engine as E, maps
+    m = maps.load_map("validation-mazes-seed-001")
+    grid = m["grid"]
+    st, gl = maps.sample_instance(m, 20, 3)
+    _, gl2 = maps.sample_instance(m, 20, 4)
+    eng = E.RolloutEngine(1, 20, *grid.shape)
+    eng.reset(0, grid, st, gl)
+    o = oracle.ObsOracle(grid)
+    o.create_agents(st, gl)
+    act = np.full(20, -1, np.int32)
+    for goals in (gl, gl2, gl2, gl):
+        eng.update_agents(st[None], goals[None], act[None])
+        o.update_agents(st, goals, act)
+        assert (eng.generate_observations()[0] == o.generate_observations()).all()
+        act = np.arange(20, dtype=np.int32) % 5
+    eng.close()
+
+
+@pytest.mark.parametrize("density,seed", [(0.2, 0), (0.6, 1), (0.95, 2)])
+def test_soft_step_kernel_vs_oracle(dev, density, seed):
+    import oracle
+    from mapf_gpt_b200 import engine as E
+    rng = np.random.default_rng(seed)
+    H, Wd, envs = 24, 27, 48
+    grid = np.ones((H, Wd), np.uint8)
+    grid[5:-5, 5:-5] = rng.random((H - 10, Wd - 10)) < 0.15
+    free = np.argwhere(grid == 0)
+    n = max(2, int(density * len(free)))
+    pos = np.stack([free[rng.permutation(len(free))[:n]] for _ in range(envs)]).astype(np.int32)
+    eng = E.RolloutEngine(envs, n, H, Wd)
+    eng.reset(0, grid, pos, pos[:, ::-1].copy())
+    for t in range(6):
+        act = rng.integers(-1, 6, (envs, n)).astype(np.int32)
+        new = eng.env_step(act)
+        for e in range(envs):
+            pos[e], _ = oracle.pogema_step_soft(grid, pos[e], act[e])
+        assert (new == pos).all(), f"step {t}"
+    met = eng.metrics()
+    assert (met[:, 0] == 6).all() and (met[:, 6] == 6 * n).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("name,tag", [("2M", "init"), ("2M", "sharp"), ("6M", "init"), ("6M", "sharp"), ("85M", "sharp")])
+def test_forward_logits_vs_reference_golden(dev, name, tag):
+    """Logits of the reference model.py (fp32, CPU) on committed tokens; tolerance LOGIT_TOL abs."""
+    from mapf_gpt_b200 import engine as E, weights as W
+    cfg = W.model_config(name)
+    sd = W.random_init(cfg, 1234)
+    if tag == "sharp":
+        sd = W.scale_weights(W.perturb_layernorm(sd), 3.0)
+    assert W.state_dict_digest(sd) == bytes(GOLD_GPT[f"{name}_{tag}_digest"]).hex()
+    eng = E.RolloutEngine(1, 1, 11, 11)
+    eng.load_model(sd, cfg)
+    lg = eng.forward_tokens(GOLD_GPT["tokens"])
+    ref = GOLD_GPT[f"{name}_{tag}_logits"][:, :5]
+    err = np.abs(lg - ref).max()
+    assert err < LOGIT_TOL, err
+    # greedy actions agree wherever the reference's top-2 margin exceeds twice the tolerance
+    srt = np.sort(ref, -1)
+    dec = (srt[:, -1] - srt[:, -2]) > 2 * LOGIT_TOL
+    assert (lg.argmax(-1)[dec] == GOLD_GPT[f"{name}_{tag}_greedy"][dec]).all()
+    eng.close()
+
+
+def test_forward_many_rows_matches_oracle_and_is_batch_invariant(dev):
+    from mapf_gpt_b200 import engine as E, weights as W
+    from oracle import gpt_oracle as G
+    cfg = W.model_config("2M")
+    sd = W.scale_weights(W.perturb_layernorm(W.random_init(cfg)), 3.0)
+    rng = np.random.default_rng(1)
+    toks = rng.integers(0, 67, (300, 256)).astype(np.int8)
+    eng = E.RolloutEngine(1, 1, 11, 11)
+    eng.load_model(sd, cfg)
+    a = eng.forward_tokens(toks)
+    b = eng.forward_tokens(toks[:7])
+    assert np.array_equal(a[:7], b)                                     # rows are independent, bitwise
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    ref = G.forward_logits(sdd, cfg.n_layer, cfg.n_head, torch.from_numpy(toks.astype(np.int64)).to(dev))[:, :5].cpu().numpy()
+    assert np.abs(a - ref).max() < LOGIT_TOL
+    eng.close()
+
+
+def test_sampler_identical_p_and_q_give_identical_actions(dev):
+    """GPT.act tail (model.py:249-257) == argmax(softmax(logits[:5]) / q)."""
+    from mapf_gpt_b200 import engine as E, maps, weights as W
+    m = maps.load_map("validation-random-seed-000")
+    n, envs = 32, 8
+    st = np.stack([maps.sample_instance(m, n, 2, e)[0] for e in range(envs)])
+    gl = np.stack([maps.sample_instance(m, n, 2, e)[1] for e in range(envs)])
+    cfg = W.model_config("2M")
+    eng = E.RolloutEngine(envs, n, *m["grid"].shape)
+    eng.load_model(W.scale_weights(W.random_init(cfg), 4.0), cfg)
+    eng.reset(0, m["grid"], st, gl)
+    eng.update_agents()
+    eng.generate_observations(fetch=False)
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.empty((envs * n, 67), device=dev).exponential_(1, generator=g)[:, :5]
+    acts, logits = eng.act(E.MODE_SUPPLIED_Q, q.cpu().numpy().reshape(envs, n, 5), want_logits=True)
+    p = torch.softmax(torch.from_numpy(logits).reshape(-1, 5).to(dev), -1)
+    want = (p / q).argmax(-1).cpu().numpy().reshape(envs, n)
+    assert (acts == want).all()
+    greedy = eng.act(E.MODE_GREEDY)
+    assert (greedy == logits.argmax(-1)).all()
+    # philox mode: deterministic in (seed, env, agent, step), different across seeds
+    eng.set_seed(5); a1 = eng.act(E.MODE_PHILOX)
+    eng.set_seed(5); a2 = eng.act(E.MODE_PHILOX)
+    eng.set_seed(6); a3 = eng.act(E.MODE_PHILOX)
+    assert (a1 == a2).all() and (a1 != a3).any()
+    eng.close()
