@@ -146,12 +146,16 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: no e2e / cpu baseline, warm-up as given")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.quick:
+        args.no_e2e = args.no_cpu_baseline = True
+    elif args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -243,7 +247,8 @@ def main():
         C, L, T = cfg.n_embd, cfg.n_layer, 256
         rows_per_launch = min(E_gpu * n, 8192) * T           # the engine forwards in chunks of 8192 sequences
         kflops = {"gemm_qkv": 2 * 3 * C * C, "gemm_attn_proj": 2 * C * C, "gemm_fc_gelu": 2 * 4 * C * C,
-                  "gemm_mlp_proj": 2 * 4 * C * C, "attention": 4 * T * C}   # per token
+                  "gemm_mlp_proj": 2 * 4 * C * C, "attention": 4 * T * C,
+                  "post_attn_fused": 2 * 9 * C * C}   # per token
         kern = {}
         for k, v in ktimes.items():
             if v["launches"]:

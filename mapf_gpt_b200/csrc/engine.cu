@@ -8,12 +8,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "../../include/mapf_gpt_b200.h"
 #include "env_kernels.cuh"
 #include "gpt_kernels.cuh"
+#include "fused_kernels.cuh"
 
 using namespace mg;
 
@@ -37,16 +39,18 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 // ------------------------------------------------------------------------------------------- model
-enum KernelClass { KC_BFS = 0, KC_OBSERVE, KC_EMBED, KC_LN, KC_QKV, KC_ATTN, KC_PROJ, KC_FC, KC_PROJ2, KC_HEAD, KC_STEP, KC_COUNT };
+enum KernelClass { KC_BFS = 0, KC_OBSERVE, KC_EMBED, KC_LN, KC_QKV, KC_ATTN, KC_PROJ, KC_FC, KC_PROJ2, KC_HEAD, KC_STEP, KC_POST, KC_COUNT };
 
 struct Layer {
     float *ln1 = nullptr, *ln2 = nullptr;
     __nv_bfloat16 *wqkv = nullptr, *wproj = nullptr, *wfc = nullptr, *wproj2 = nullptr;
+    __nv_bfloat16 *wstream = nullptr;   // fused post-attention kernel: stage images in consumption order
 };
 struct Model {
     bool loaded = false;
     mg_model_config cfg{};
     int BN = 0, BK = 0, hs = 0;
+    bool fused = false;   // C in {160, 256}: post_attn_kernel replaces proj / ln_2 / fc / proj2 / next ln_1
     float *wte = nullptr, *wpe = nullptr, *lnf = nullptr;
     std::vector<Layer> layers;
 };
@@ -149,6 +153,65 @@ static int upload_f32(const float *src, size_t n, float **out)
     return MG_OK;
 }
 
+// Stage stream of post_attn_kernel<C> (fused_kernels.cuh): proj k-steps, then FC(0), FC(1), P2(0), FC(2), ...
+// Wproj[C][C], Wfc[4C][C], Wproj2[C][4C] are torch Linear weights (row = output feature).
+static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, int C, __nv_bfloat16 **out)
+{
+    const int HC = C / 2, NCH = 8, NPROJ = C / 16, NFC = C / 32, NP2 = HC / 16;
+    const size_t stage_elems = (size_t)16 * C;   // 32*C bytes
+    const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2)) * stage_elems;
+    std::vector<uint16_t> h(total, 0);
+    size_t st = 0;
+    auto put_kn = [&](size_t base, int kc, int rows, int n, int k8, float v) {   // [kc][rows][8]
+        h[base + ((size_t)kc * rows + n) * 8 + k8] = f2bf(v);
+    };
+    for (int ks = 0; ks < NPROJ; ks++, st++)
+        for (int n = 0; n < C; n++)
+            for (int k = 0; k < 16; k++) put_kn(st * stage_elems, k / 8, C, n, k % 8, Wproj[(size_t)n * C + ks * 16 + k]);
+    auto put_fc = [&](int j) {
+        for (int kb = 0; kb < NFC; kb++, st++)
+            for (int n = 0; n < HC; n++)
+                for (int k = 0; k < 32; k++)
+                    put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wfc[(size_t)(j * HC + n) * C + kb * 32 + k]);
+    };
+    auto put_p2 = [&](int j) {
+        for (int ks = 0; ks < NP2; ks++, st++)
+            for (int n = 0; n < C; n++)
+                for (int k = 0; k < 16; k++)
+                    put_kn(st * stage_elems, k / 8, C, n, k % 8, Wproj2[(size_t)n * 4 * C + j * HC + ks * 16 + k]);
+    };
+    put_fc(0);
+    for (int j = 0; j < NCH; j++) {
+        if (j + 1 < NCH) put_fc(j + 1);
+        put_p2(j);
+    }
+    CU(dalloc(out, total));
+    CU(cudaMemcpy(*out, h.data(), total * 2, cudaMemcpyHostToDevice));
+    return MG_OK;
+}
+
+template <int C>
+static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT)
+{
+    constexpr int smem = PostAttnCfg<C>::SMEM_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(post_attn_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    prof_begin(e, KC_POST);
+    post_attn_kernel<C><<<MT, 320, smem, e->stream>>>(a);
+    prof_end(e);
+    CU(cudaGetLastError());
+    return MG_OK;
+}
+static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT)
+{
+    if (C == 160) return launch_post_attn_c<160>(e, a, MT);
+    if (C == 256) return launch_post_attn_c<256>(e, a, MT);
+    return fail(MG_ERR_ARG, "post_attn: unsupported width %d", C);
+}
+
 // ------------------------------------------------------------------------------------------- GEMM dispatch
 template <int BN, int BK, int STAGES, int EPI>
 static int launch_gemm_cfg(mg_engine *e, const GemmArgs &a, int kc)
@@ -236,6 +299,31 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
     for (int s0 = 0; s0 < n_seq; s0 += w.chunk_seqs) {
         const int ns = std::min(w.chunk_seqs, n_seq - s0);
         const int M = ns * 256, MT = M / 128;
+        if (m.fused) {
+            prof_begin(e, KC_EMBED);
+            embed_ln_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, m.layers[0].ln1, w.X, w.XN, C);
+            prof_end(e);
+            for (int l = 0; l < m.cfg.n_layer; l++) {
+                const Layer &L = m.layers[l];
+                GemmArgs g{};
+                g.A = w.XN; g.W = L.wqkv; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
+                if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
+                AttnArgs at{};
+                at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
+                at.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
+                if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
+                PostAttnArgs pa{};
+                pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;
+                const bool last = l + 1 == m.cfg.n_layer;
+                pa.next_gain = last ? nullptr : m.layers[l + 1].ln1;
+                pa.xn_out = last ? nullptr : w.XN;
+                if ((rc = launch_post_attn(e, C, pa, MT))) return rc;
+            }
+            prof_begin(e, KC_HEAD);
+            head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.X, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
+            prof_end(e);
+            continue;
+        }
         prof_begin(e, KC_EMBED);
         embed_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, C);
         prof_end(e);
@@ -408,7 +496,7 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(e->d_metrics);
     Model &m = e->model;
     cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf);
-    for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); }
+    for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
     for (auto &p : e->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -448,19 +536,25 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
     if ((rc = upload_f32(w, (size_t)256 * C, &m.wpe))) return rc;
     w += (size_t)256 * C;
     m.layers.resize(cfg->n_layer);
+    const char *force_generic = getenv("MAPF_GPT_B200_GENERIC");
+    m.fused = (C == 160 || C == 256) && !(force_generic && force_generic[0] == '1');
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;
         if ((rc = upload_packed(w, 3 * C, C, BN, &L.wqkv))) return rc;
         w += 3 * CC;
+        const float *wproj = w;
         if ((rc = upload_packed(w, C, C, BN, &L.wproj))) return rc;
         w += CC;
         if ((rc = upload_f32(w, C, &L.ln2))) return rc;
         w += C;
+        const float *wfc = w;
         if ((rc = upload_packed(w, 4 * C, C, BN, &L.wfc))) return rc;
         w += 4 * CC;
+        const float *wproj2 = w;
         if ((rc = upload_packed(w, C, 4 * C, BN, &L.wproj2))) return rc;
         w += 4 * CC;
+        if (m.fused && (rc = upload_post_attn_stream(wproj, wfc, wproj2, C, &L.wstream))) return rc;
     }
     if ((rc = upload_f32(w, C, &m.lnf))) return rc;
     m.loaded = true;

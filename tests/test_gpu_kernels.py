@@ -195,3 +195,23 @@ def test_sampler_identical_p_and_q_give_identical_actions(dev):
     eng.set_seed(6); a3 = eng.act(E.MODE_PHILOX)
     assert (a1 == a2).all() and (a1 != a3).any()
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["2M", "6M"])
+def test_fused_and_generic_paths_agree(dev, name, monkeypatch):
+    """C in {160, 256}: post_attn_kernel (fused proj+LN2+MLP+next LN1) vs the five separate kernels."""
+    from mapf_gpt_b200 import engine as E, weights as W
+    cfg = W.model_config(name)
+    sd = W.scale_weights(W.perturb_layernorm(W.random_init(cfg)), 3.0)
+    toks = np.random.default_rng(3).integers(0, 67, (70, 256)).astype(np.int8)
+    outs = []
+    for generic in ("0", "1"):
+        monkeypatch.setenv("MAPF_GPT_B200_GENERIC", generic)
+        eng = E.RolloutEngine(1, 1, 11, 11)
+        eng.load_model(sd, cfg)
+        outs.append(eng.forward_tokens(toks))
+        eng.close()
+    assert np.abs(outs[0] - outs[1]).max() < 2e-2       # same bf16 operands; GELU polynomial vs erff, LN pass order
+    from oracle import gpt_oracle as G
+    ref = G.forward_logits(sd, cfg.n_layer, cfg.n_head, torch.from_numpy(toks.astype(np.int64)))[:, :5].numpy()
+    assert np.abs(outs[0] - ref).max() < LOGIT_TOL and np.abs(outs[1] - ref).max() < LOGIT_TOL

@@ -130,7 +130,8 @@ def test_ragged_slots_and_edge_cases(built):
         orcs[e].update_agents(sts[e], gls[e], np.full(n, -1, np.int32))
         assert (toks[e, :n] == orcs[e].generate_observations()).all()
     acts = eng.act(E.MODE_GREEDY)
-    assert acts.shape == (3, 12) and ((acts >= 0) & (acts <= 4)).all()
+    assert acts.shape == (3, 12)
+    assert all(((acts[e, :n] >= 0) & (acts[e, :n] <= 4)).all() and (acts[e, n:] == -1).all() for e, n in enumerate(ns))
     eng.env_step(None)
     met = eng.metrics()
     assert met[:, 7].tolist() == [12, 1, 5] and met[2, 5] >= 0
