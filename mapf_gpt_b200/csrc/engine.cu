@@ -52,6 +52,7 @@ struct Model {
     int BN = 0, BK = 0, hs = 0;
     bool fused = false;   // C in {160, 256}: post_attn_kernel replaces proj / ln_2 / fc / proj2 / next ln_1
     float *wte = nullptr, *wpe = nullptr, *lnf = nullptr;
+    float *wpe_ti = nullptr;   // wpe re-tiled [2][C/4][128][4] for embed_ln_kernel
     std::vector<Layer> layers;
 };
 struct Workspace {
@@ -256,7 +257,7 @@ static int launch_attn_hs(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream
         attr_set = true;
     }
     if (e) prof_begin(e, KC_ATTN);
-    attn_kernel<HS><<<n_seq * a.n_head * 2, 160, smem, st>>>(a);
+    attn_kernel<HS><<<n_seq * a.n_head * 2, 288, smem, st>>>(a);
     if (e) prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
@@ -301,7 +302,8 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         const int M = ns * 256, MT = M / 128;
         if (m.fused) {
             prof_begin(e, KC_EMBED);
-            embed_ln_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, m.layers[0].ln1, w.X, w.XN, C);
+            embed_ln_kernel<<<MT, 128, 67 * (C + 4) * 4, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe_ti, m.layers[0].ln1,
+                                                                      w.X, w.XN, C);
             prof_end(e);
             for (int l = 0; l < m.cfg.n_layer; l++) {
                 const Layer &L = m.layers[l];
@@ -495,7 +497,7 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(e->d_pos_in); cudaFree(e->d_goal_in); cudaFree(e->d_act_in); cudaFree(e->d_step_act); cudaFree(e->d_q);
     cudaFree(e->d_metrics);
     Model &m = e->model;
-    cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf);
+    cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti);
     for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
@@ -534,6 +536,14 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
     if ((rc = upload_f32(w, (size_t)MG_VOCAB * C, &m.wte))) return rc;
     w += (size_t)MG_VOCAB * C;
     if ((rc = upload_f32(w, (size_t)256 * C, &m.wpe))) return rc;
+    {
+        std::vector<float> ti((size_t)256 * C);
+        for (int pos = 0; pos < 256; pos++)
+            for (int c = 0; c < C; c++)
+                ti[(((size_t)(pos >> 7) * (C / 4) + c / 4) * 128 + (pos & 127)) * 4 + (c & 3)] = w[(size_t)pos * C + c];
+        if ((rc = upload_f32(ti.data(), ti.size(), &m.wpe_ti))) return rc;
+        CU(cudaFuncSetAttribute(embed_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 67 * (768 + 4) * 4));
+    }
     w += (size_t)256 * C;
     m.layers.resize(cfg->n_layer);
     const char *force_generic = getenv("MAPF_GPT_B200_GENERIC");

@@ -31,24 +31,47 @@ struct PostAttnArgs {
     __nv_bfloat16 *xn_out;         // A_ti for the next block's QKV GEMM, or nullptr
 };
 
-// erf-GELU with an odd degree-19 polynomial for erf on |z| <= 3 (|erf error| < 2e-5 in fp32, then clamped):
-// FMA-only, no MUFU.  The result is rounded to bf16 (rel. 4e-3) right after, see DESIGN.md "Tolerance".
-__device__ __forceinline__ float gelu_poly(float x)
+// erf-GELU on a PAIR of values with packed fp32x2 math (FFMA2): erf(z) ~ z * P(z^2), odd degree-17 polynomial on
+// |z| <= 3 (z clamped by one saturating FFMA per element), FMA-only, no MUFU.  Max |gelu error| 5e-5 over all x;
+// the result is rounded to bf16 (rel. 4e-3) right after, see DESIGN.md "Tolerance".
+__device__ __forceinline__ f32x2 gelu2(float x0, float x1)
 {
-    float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
-    const float u = z * z;
-    float p = -3.6272167491802065e-09f;
-    p = fmaf(p, u, 1.9419158547862025e-07f);
-    p = fmaf(p, u, -4.674287538364297e-06f);
-    p = fmaf(p, u, 6.756548100383952e-05f);
-    p = fmaf(p, u, -0.0006636687321588397f);
-    p = fmaf(p, u, 0.004765239544212818f);
-    p = fmaf(p, u, -0.026179470121860504f);
-    p = fmaf(p, u, 0.11225908994674683f);
-    p = fmaf(p, u, -0.3758990168571472f);
-    p = fmaf(p, u, 1.1283525228500366f);
-    const float hx = 0.5f * x;
-    return fmaf(hx, z * p, hx);
+    const float w0 = __saturatef(fmaf(x0, 0.70710678118654752440f / 6.0f, 0.5f));
+    const float w1 = __saturatef(fmaf(x1, 0.70710678118654752440f / 6.0f, 0.5f));
+    const f32x2 z = fma2(pk2(w0, w1), pk2(6.0f, 6.0f), pk2(-3.0f, -3.0f));
+    const f32x2 u = mul2(z, z);
+    f32x2 p = pk2(3.9138299712249136e-08f, 3.9138299712249136e-08f);
+    p = fma2(p, u, pk2(-1.8835556829799316e-06f, -1.8835556829799316e-06f));
+    p = fma2(p, u, pk2(4.0097045712172985e-05f, 4.0097045712172985e-05f));
+    p = fma2(p, u, pk2(-0.0005030000465922058f, -0.0005030000465922058f));
+    p = fma2(p, u, pk2(0.004197265952825546f, 0.004197265952825546f));
+    p = fma2(p, u, pk2(-0.02500014565885067f, -0.02500014565885067f));
+    p = fma2(p, u, pk2(0.11093290150165558f, 0.11093290150165558f));
+    p = fma2(p, u, pk2(-0.3752213716506958f, -0.3752213716506958f));
+    p = fma2(p, u, pk2(1.128251075744629f, 1.128251075744629f));
+    const f32x2 hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
+    return fma2(hx, mul2(z, p), hx);
+}
+
+// (v - mean) * rstd * gain for 8 consecutive columns -> 8 bf16 (one 16-byte store); a = rstd, b = -mean * rstd
+__device__ __forceinline__ uint4 ln_pack8(const uint32_t *v, f32x2 a, f32x2 b, const float4 g0, const float4 g1)
+{
+    uint4 o;
+    o.x = pack_bf16x2_p(mul2(fma2(pk2u(v[0], v[1]), a, b), pk2(g0.x, g0.y)));
+    o.y = pack_bf16x2_p(mul2(fma2(pk2u(v[2], v[3]), a, b), pk2(g0.z, g0.w)));
+    o.z = pack_bf16x2_p(mul2(fma2(pk2u(v[4], v[5]), a, b), pk2(g1.x, g1.y)));
+    o.w = pack_bf16x2_p(mul2(fma2(pk2u(v[6], v[7]), a, b), pk2(g1.z, g1.w)));
+    return o;
+}
+// sum of squared deviations of 16 values, packed
+__device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean, f32x2 acc)
+{
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        const f32x2 d = add2(pk2u(v[j], v[j + 1]), negmean);
+        acc = fma2(d, d, acc);
+    }
+    return acc;
 }
 
 template <int C>
@@ -204,6 +227,7 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
         {
             const float4 *Xg = reinterpret_cast<const float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
             float sum = 0.f;
+            f32x2 sum2 = pk2(0.f, 0.f);
 #pragma unroll 1
             for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
                 uint32_t v[16];
@@ -214,33 +238,40 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float e0 = __uint_as_float(v[4 * j + 0]) + xv[j].x, e1 = __uint_as_float(v[4 * j + 1]) + xv[j].y;
-                    const float e2 = __uint_as_float(v[4 * j + 2]) + xv[j].z, e3 = __uint_as_float(v[4 * j + 3]) + xv[j].w;
-                    v[4 * j + 0] = __float_as_uint(e0); v[4 * j + 1] = __float_as_uint(e1);
-                    v[4 * j + 2] = __float_as_uint(e2); v[4 * j + 3] = __float_as_uint(e3);
-                    sum += (e0 + e1) + (e2 + e3);
+                    const f32x2 e0 = add2(pk2u(v[4 * j + 0], v[4 * j + 1]), pk2(xv[j].x, xv[j].y));
+                    const f32x2 e1 = add2(pk2u(v[4 * j + 2], v[4 * j + 3]), pk2(xv[j].z, xv[j].w));
+                    upk2u(e0, v[4 * j + 0], v[4 * j + 1]);
+                    upk2u(e1, v[4 * j + 2], v[4 * j + 3]);
+                    sum2 = add2(sum2, add2(e0, e1));
                 }
                 tmem_st16(trow + c0, v);
             }
             tmem_wait_st();
+            {
+                float s0, s1;
+                upk2(sum2, s0, s1);
+                sum = s0 + s1;
+            }
             red_s[h * 128 + r] = sum;
             named_bar_sync(1, 256);
             const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
-            float sq = 0.f;
+            f32x2 sq2 = pk2(0.f, 0.f);
+            const f32x2 negmean = pk2(-mean, -mean);
 #pragma unroll 1
             for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(trow + c0, v);
                 tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const float d = __uint_as_float(v[j]) - mean;
-                    sq = fmaf(d, d, sq);
-                }
+                sq2 = sqdev16(v, negmean, sq2);
             }
-            red_q[h * 128 + r] = sq;
+            {
+                float s0, s1;
+                upk2(sq2, s0, s1);
+                red_q[h * 128 + r] = s0 + s1;
+            }
             named_bar_sync(1, 256);
             const float rstd = rsqrtf((red_q[r] + red_q[128 + r]) * inv_c + 1e-5f);
+            const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
             const float4 *g4 = reinterpret_cast<const float4 *>(a.ln2_gain);
 #pragma unroll 1
             for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
@@ -248,15 +279,9 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 tmem_ld16(trow + c0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const float4 g0 = __ldg(g4 + c0 / 4 + 2 * j), g1 = __ldg(g4 + c0 / 4 + 2 * j + 1);
-                    uint4 o;
-                    o.x = pack_bf16x2((__uint_as_float(v[8 * j + 0]) - mean) * rstd * g0.x, (__uint_as_float(v[8 * j + 1]) - mean) * rstd * g0.y);
-                    o.y = pack_bf16x2((__uint_as_float(v[8 * j + 2]) - mean) * rstd * g0.z, (__uint_as_float(v[8 * j + 3]) - mean) * rstd * g0.w);
-                    o.z = pack_bf16x2((__uint_as_float(v[8 * j + 4]) - mean) * rstd * g1.x, (__uint_as_float(v[8 * j + 5]) - mean) * rstd * g1.y);
-                    o.w = pack_bf16x2((__uint_as_float(v[8 * j + 6]) - mean) * rstd * g1.z, (__uint_as_float(v[8 * j + 7]) - mean) * rstd * g1.w);
-                    *reinterpret_cast<uint4 *>(As + ((c0 / 8 + j) * 128 + r) * 16) = o;
-                }
+                for (int j = 0; j < 2; j++)
+                    *reinterpret_cast<uint4 *>(As + ((c0 / 8 + j) * 128 + r) * 16) =
+                        ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -282,10 +307,10 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
 #pragma unroll
             for (int g = 0; g < NV; g++) {
                 uint4 o;
-                o.x = pack_bf16x2(gelu_poly(__uint_as_float(v[g][0])), gelu_poly(__uint_as_float(v[g][1])));
-                o.y = pack_bf16x2(gelu_poly(__uint_as_float(v[g][2])), gelu_poly(__uint_as_float(v[g][3])));
-                o.z = pack_bf16x2(gelu_poly(__uint_as_float(v[g][4])), gelu_poly(__uint_as_float(v[g][5])));
-                o.w = pack_bf16x2(gelu_poly(__uint_as_float(v[g][6])), gelu_poly(__uint_as_float(v[g][7])));
+                o.x = pack_bf16x2_p(gelu2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1])));
+                o.y = pack_bf16x2_p(gelu2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3])));
+                o.z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
+                o.w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
                 *reinterpret_cast<uint4 *>(Hb + ((h * NV + g) * 128 + r) * 16) = o;
             }
             fence_proxy_async_smem();
@@ -315,21 +340,23 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 red_s[h * 128 + r] = sum;
                 named_bar_sync(1, 256);
                 const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
-                float sq = 0.f;
+                f32x2 sq2 = pk2(0.f, 0.f);
+                const f32x2 negmean = pk2(-mean, -mean);
 #pragma unroll 1
                 for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(trow + c0, v);
                     tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const float d = __uint_as_float(v[j]) - mean;
-                        sq = fmaf(d, d, sq);
-                    }
+                    sq2 = sqdev16(v, negmean, sq2);
                 }
-                red_q[h * 128 + r] = sq;
+                {
+                    float s0, s1;
+                    upk2(sq2, s0, s1);
+                    red_q[h * 128 + r] = s0 + s1;
+                }
                 named_bar_sync(1, 256);
                 const float rstd = rsqrtf((red_q[r] + red_q[128 + r]) * inv_c + 1e-5f);
+                const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
                 const float4 *g4 = reinterpret_cast<const float4 *>(a.next_gain);
                 uint4 *O = reinterpret_cast<uint4 *>(a.xn_out) + (size_t)mt * (C / 8) * 128 + r;
 #pragma unroll 1
@@ -338,15 +365,9 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                     tmem_ld16(trow + c0, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const float4 g0 = __ldg(g4 + c0 / 4 + 2 * j), g1 = __ldg(g4 + c0 / 4 + 2 * j + 1);
-                        uint4 o;
-                        o.x = pack_bf16x2((__uint_as_float(v[8 * j + 0]) - mean) * rstd * g0.x, (__uint_as_float(v[8 * j + 1]) - mean) * rstd * g0.y);
-                        o.y = pack_bf16x2((__uint_as_float(v[8 * j + 2]) - mean) * rstd * g0.z, (__uint_as_float(v[8 * j + 3]) - mean) * rstd * g0.w);
-                        o.z = pack_bf16x2((__uint_as_float(v[8 * j + 4]) - mean) * rstd * g1.x, (__uint_as_float(v[8 * j + 5]) - mean) * rstd * g1.y);
-                        o.w = pack_bf16x2((__uint_as_float(v[8 * j + 6]) - mean) * rstd * g1.z, (__uint_as_float(v[8 * j + 7]) - mean) * rstd * g1.w);
-                        O[(size_t)(c0 / 8 + j) * 128] = o;
-                    }
+                    for (int j = 0; j < 2; j++)
+                        O[(size_t)(c0 / 8 + j) * 128] =
+                            ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
                 }
             }
         }
@@ -356,21 +377,28 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
     if (warp == 9) tmem_dealloc<K::TMEM_COLS>(tmem);
 }
 
-// embedding + ln_1 of block 0 in one pass (model.py:171-175 + model.py:102): X_ti and A_ti out
+// embedding + ln_1 of block 0 in one pass (model.py:171-175 + model.py:102): X_ti and A_ti out.
+// thread == row.  wte (67 x C fp32) is staged in shared memory with a padded row pitch (random token rows would
+// otherwise hit the same banks); wpe arrives pre-tiled ([2][C/4][128][4]) so position rows are coalesced loads.
 __global__ void __launch_bounds__(128) embed_ln_kernel(const uint8_t *__restrict__ tokens, const float *__restrict__ wte,
-                                                       const float *__restrict__ wpe, const float *__restrict__ gain,
+                                                       const float *__restrict__ wpe_ti, const float *__restrict__ gain,
                                                        float *__restrict__ X, __nv_bfloat16 *__restrict__ XN, int C)
 {
+    extern __shared__ __align__(16) float wte_s[];      // [67][C + 4]
+    const int pitch = C + 4;
+    for (int i = threadIdx.x; i < 67 * (C / 4); i += 128) {
+        const int row = i / (C / 4), c4 = i - row * (C / 4);
+        *reinterpret_cast<float4 *>(wte_s + row * pitch + c4 * 4) = __ldg(reinterpret_cast<const float4 *>(wte) + i);
+    }
+    __syncthreads();
     const int mt = blockIdx.x, r = threadIdx.x;
-    const size_t row = (size_t)mt * 128 + r;
-    const int tok = tokens[row];
-    const int pos = (int)(row & 255);
-    const float4 *te = reinterpret_cast<const float4 *>(wte + (size_t)tok * C);
-    const float4 *pe = reinterpret_cast<const float4 *>(wpe + (size_t)pos * C);
+    const int tok = tokens[(size_t)mt * 128 + r];
+    const float4 *te = reinterpret_cast<const float4 *>(wte_s + tok * pitch);
+    const float4 *pe = reinterpret_cast<const float4 *>(wpe_ti) + (size_t)(mt & 1) * (C / 4) * 128 + r;
     float4 *Xo = reinterpret_cast<float4 *>(X) + (size_t)mt * (C / 4) * 128 + r;
     float s = 0.f;
     for (int c4 = 0; c4 < C / 4; c4++) {
-        const float4 t = __ldg(te + c4), p = __ldg(pe + c4);
+        const float4 t = te[c4], p = __ldg(pe + (size_t)c4 * 128);
         const float4 v = make_float4(t.x + p.x, t.y + p.y, t.z + p.z, t.w + p.w);
         Xo[(size_t)c4 * 128] = v;
         s += (v.x + v.y) + (v.z + v.w);
@@ -378,7 +406,7 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(const uint8_t *__restrict
     const float mean = s / (float)C;
     float q = 0.f;
     for (int c4 = 0; c4 < C / 4; c4++) {
-        const float4 t = __ldg(te + c4), p = __ldg(pe + c4);
+        const float4 t = te[c4], p = __ldg(pe + (size_t)c4 * 128);
         const float a0 = t.x + p.x - mean, a1 = t.y + p.y - mean, a2 = t.z + p.z - mean, a3 = t.w + p.w - mean;
         q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     }
@@ -386,7 +414,8 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(const uint8_t *__restrict
     uint4 *O = reinterpret_cast<uint4 *>(XN) + (size_t)mt * (C / 8) * 128 + r;
     const float4 *g4 = reinterpret_cast<const float4 *>(gain);
     for (int c8 = 0; c8 < C / 8; c8++) {
-        const float4 t0 = __ldg(te + 2 * c8), p0 = __ldg(pe + 2 * c8), t1 = __ldg(te + 2 * c8 + 1), p1 = __ldg(pe + 2 * c8 + 1);
+        const float4 t0 = te[2 * c8], p0 = __ldg(pe + (size_t)(2 * c8) * 128);
+        const float4 t1 = te[2 * c8 + 1], p1 = __ldg(pe + (size_t)(2 * c8 + 1) * 128);
         const float4 g0 = __ldg(g4 + 2 * c8), g1 = __ldg(g4 + 2 * c8 + 1);
         uint4 o;
         o.x = pack_bf16x2((t0.x + p0.x - mean) * rstd * g0.x, (t0.y + p0.y - mean) * rstd * g0.y);

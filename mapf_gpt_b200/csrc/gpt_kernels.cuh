@@ -43,11 +43,20 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
     uint64_t *empty = full + STAGES;
     uint64_t *acc_bar = empty + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+    uint32_t *qkv_off = tmem_slot + 2;   // EPI_QKV: uint4 offset of each 8-column group inside a sequence's q/k/v block
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = a.N / BN;
     const int nt = blockIdx.x % NT, mt = blockIdx.x / NT;
     const int KB = a.K / BK;
+    if constexpr (EPI == EPI_QKV) {
+        if (threadIdx.x < BN / 8) {
+            const int n = nt * BN + 8 * threadIdx.x;
+            const int which = n / a.C, rem = n - which * a.C;
+            const int head = rem / a.hs, d0 = rem - head * a.hs;
+            qkv_off[threadIdx.x] = (uint32_t)(((which * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256);
+        }
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -142,19 +151,15 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
                 }
             } else {  // EPI_QKV: scatter into [seq][3][head][hs/8][256][8]
                 const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
+                uint4 *Oseq = reinterpret_cast<uint4 *>(a.out) + (size_t)seq * (3 * a.C / 8) * 256 + tok;
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const int n = n0 + 8 * j;
-                    const int which = n / a.C, rem = n - which * a.C;
-                    const int head = rem / a.hs, d0 = rem - head * a.hs;
                     uint4 o;
                     o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
                     o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
                     o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
                     o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                    uint4 *O = reinterpret_cast<uint4 *>(a.out) +
-                               ((((size_t)seq * 3 + which) * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256 + tok;
-                    *O = o;
+                    Oseq[qkv_off[c0 / 8 + j]] = o;
                 }
             }
         }
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
 }
 
 template <int BN, int BK, int STAGES>
-constexpr int gemm_smem_bytes() { return STAGES * (BK * 256 + BK * BN * 2) + (2 * STAGES + 1) * 8 + 16; }
+constexpr int gemm_smem_bytes() { return STAGES * (BK * 256 + BK * BN * 2) + (2 * STAGES + 1) * 8 + 16 + (BN / 8) * 4; }
 
 // ---------------------------------------------------------------------------------------------
 // Non-causal attention for one (sequence, head, 128-query tile): S = Q K^T (M128,N256,K=hs) in
@@ -189,13 +194,24 @@ __device__ __forceinline__ float ex2_approx(float x)
     return y;
 }
 
-template <int HS>
-__global__ void __launch_bounds__(160) attn_kernel(const AttnArgs a)
+__device__ __forceinline__ float max3(float a, float b, float c)
 {
-    constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = 256 * HS * 2, P_BYTES = 128 * 256 * 2;
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+    return r;
+}
+
+// warps 0-7: softmax (thread pair per query row: TMEM lane quadrant = warp&3, key half = warp>>2) + epilogue,
+// warp 8: bulk copies + UMMA issue.  V carries 16 extra columns of ones so that the P V UMMA also produces the
+// row sum of the (bf16-rounded) probabilities in TMEM column HS -- no per-element add in the softmax loop.
+template <int HS>
+__global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const AttnArgs a)
+{
+    constexpr int Q_BYTES = 128 * HS * 2, K_BYTES = 256 * HS * 2, V_BYTES = 256 * (HS + 16) * 2, P_BYTES = 128 * 256 * 2;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *Qs = smem, *Ks = Qs + Q_BYTES, *Vs = Ks + KV_BYTES, *Ps = Vs + KV_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Ps + P_BYTES);  // QK, V, S, P, O
+    uint8_t *Qs = smem, *Ks = Qs + Q_BYTES, *Vs = Ks + K_BYTES, *Ps = Vs + V_BYTES;
+    float *redm = reinterpret_cast<float *>(Qs);                    // [2][128]; Q is dead once S = Q K^T has retired
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Ps + P_BYTES);    // QK, V, S, P, O
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,29 +223,36 @@ __global__ void __launch_bounds__(160) attn_kernel(const AttnArgs a)
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
-        mbar_init(&bars[3], 128);
+        mbar_init(&bars[3], 256);
         mbar_init(&bars[4], 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc<256>(tmem_slot);
+    if (warp == 8) tmem_alloc<256>(tmem_slot);
+    if (threadIdx.x < 256) {   // ones block of V: d-chunks HS/8 and HS/8+1, all 256 keys
+        const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        uint4 *o = reinterpret_cast<uint4 *>(Vs + K_BYTES);
+        o[threadIdx.x] = ones;
+        o[256 + threadIdx.x] = ones;
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             const size_t blk = (size_t)(HS / 8) * 256 * 8;  // elements per (seq, which, head)
             const __nv_bfloat16 *Qg = a.qkv + (((size_t)seq * 3 + 0) * a.n_head + head) * blk;
             const __nv_bfloat16 *Kg = a.qkv + (((size_t)seq * 3 + 1) * a.n_head + head) * blk;
             const __nv_bfloat16 *Vg = a.qkv + (((size_t)seq * 3 + 2) * a.n_head + head) * blk;
-            mbar_expect_tx(&bars[0], Q_BYTES + KV_BYTES);
+            mbar_expect_tx(&bars[0], Q_BYTES + K_BYTES);
 #pragma unroll
             for (int c = 0; c < HS / 8; c++)
                 bulk_g2s(Qs + c * 2048, Qg + ((size_t)c * 256 + qt * 128) * 8, 2048, &bars[0]);
-            bulk_g2s(Ks, Kg, KV_BYTES, &bars[0]);
-            mbar_expect_tx(&bars[1], KV_BYTES);
-            bulk_g2s(Vs, Vg, KV_BYTES, &bars[1]);
+            bulk_g2s(Ks, Kg, K_BYTES, &bars[0]);
+            mbar_expect_tx(&bars[1], K_BYTES);
+            bulk_g2s(Vs, Vg, K_BYTES, &bars[1]);
 
             // S = Q K^T
             mbar_wait(&bars[0], 0);
@@ -238,65 +261,60 @@ __global__ void __launch_bounds__(160) attn_kernel(const AttnArgs a)
                 constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
                 const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
 #pragma unroll
-                for (int ks = 0; ks < HS / 16; ks++) {
-                    const uint64_t ad = umma_desc(qa + ks * 2 * 2048, 2048, 128);
-                    const uint64_t bd = umma_desc(ka + ks * 2 * 4096, 4096, 128);
-                    umma_ss(tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
-                }
+                for (int ks = 0; ks < HS / 16; ks++)
+                    umma_ss(tmem, umma_desc(qa + ks * 2 * 2048, 2048, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128), idesc,
+                            ks != 0 ? 1u : 0u);
                 umma_commit(&bars[2]);
             }
-            // O = P V   (B = V, MN-major: 16 B = 8 d of one key; keys 16 B apart; d-chunks 4096 B apart)
+            // [O | rowsum] = P [V | 1]   (B MN-major: 16 B = 8 d of one key; keys 16 B apart; d-chunks 4096 B apart)
             mbar_wait(&bars[3], 0);
             mbar_wait(&bars[1], 0);
             tc_fence_after();
             {
-                constexpr uint32_t idesc = umma_idesc_bf16(128, HS, 0, 1);
+                constexpr uint32_t idesc = umma_idesc_bf16(128, HS + 16, 0, 1);
                 const uint32_t pa = smem_u32(Ps), va = smem_u32(Vs);
-                uint32_t lboV = 128, sboV = 4096;
-                if (a.dbg_variant & 1) { lboV = 4096; sboV = 128; }
 #pragma unroll
-                for (int ks = 0; ks < 16; ks++) {
-                    const uint64_t ad = umma_desc(pa + ks * 2 * 2048, 2048, 128);
-                    const uint64_t bd = umma_desc(va + ks * 2 * 128, lboV, sboV);
-                    umma_ss(tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
-                }
+                for (int ks = 0; ks < 16; ks++)
+                    umma_ss(tmem, umma_desc(pa + ks * 2 * 2048, 2048, 128), umma_desc(va + ks * 2 * 128, 128, 4096), idesc,
+                            ks != 0 ? 1u : 0u);
                 umma_commit(&bars[4]);
             }
         }
     } else {
-        const int r = threadIdx.x;  // query row within the tile
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const int q = warp & 3, kh = warp >> 2;
+        const int r = q * 32 + lane;  // query row within the tile
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         mbar_wait(&bars[2], 0);
         tc_fence_after();
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(trow + c0, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
         }
+        redm[kh * 128 + r] = mx;
+        named_bar_sync(1, 256);
+        mx = fmaxf(redm[r], redm[128 + r]);
         const float moff = mx * a.scale_log2e;
-        float sum = 0.f;
+        const f32x2 sc2 = pk2(a.scale_log2e, a.scale_log2e), mo2 = pk2(-moff, -moff);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(trow + c0, v);
             tmem_wait_ld();
-            float p[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                p[j] = ex2_approx(fmaf(__uint_as_float(v[j]), a.scale_log2e, -moff));
-                sum += p[j];
-            }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                uint4 o;
-                o.x = pack_bf16x2(p[8 * j + 0], p[8 * j + 1]);
-                o.y = pack_bf16x2(p[8 * j + 2], p[8 * j + 3]);
-                o.z = pack_bf16x2(p[8 * j + 4], p[8 * j + 5]);
-                o.w = pack_bf16x2(p[8 * j + 6], p[8 * j + 7]);
+                uint32_t w[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    float e0, e1;
+                    upk2(fma2(pk2u(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), sc2, mo2), e0, e1);   // one FFMA2 per two scores
+                    w[t] = pack_bf16x2(ex2_approx(e0), ex2_approx(e1));
+                }
+                const uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4 *>(Ps + ((c0 / 8 + j) * 128 + r) * 16) = o;
             }
         }
@@ -306,33 +324,39 @@ __global__ void __launch_bounds__(160) attn_kernel(const AttnArgs a)
 
         mbar_wait(&bars[4], 0);
         tc_fence_after();
-        const float inv = 1.0f / sum;
+        uint32_t sv[8];
+        tmem_ld8(trow + HS, sv);               // row sum (all 16 extra columns hold it)
+        constexpr int DH = HS / 2;             // output columns per thread
+        uint32_t v[DH];
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+            uint32_t t[16];
+            tmem_ld16(trow + kh * DH + c0, t);
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[c0 + j] = t[j];
+        }
+        tmem_wait_ld();
+        const float inv = 1.0f / __uint_as_float(sv[0]);
         const int mt = seq * 2 + qt;
 #pragma unroll
-        for (int c0 = 0; c0 < HS; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c0, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                uint4 o;
-                o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-                o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-                o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-                o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-                const int col = head * HS + c0 + 8 * j;
-                uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
-                *O = o;
-            }
+        for (int j = 0; j < DH / 8; j++) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+            const int col = head * HS + kh * DH + 8 * j;
+            uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
+            *O = o;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<256>(tmem);
+    if (warp == 8) tmem_dealloc<256>(tmem);
 }
 
 template <int HS>
-constexpr int attn_smem_bytes() { return 128 * HS * 2 + 2 * 256 * HS * 2 + 128 * 256 * 2 + 5 * 8 + 16; }
+constexpr int attn_smem_bytes() { return 128 * HS * 2 + 256 * HS * 2 + 256 * (HS + 16) * 2 + 128 * 256 * 2 + 5 * 8 + 16; }
 
 // ---------------------------------------------------------------------------------------------
 // Elementwise / row kernels (HBM-bound).  thread == row.
