@@ -40,6 +40,15 @@ def flops_per_agent_step(L, C, T=256, V=67):
     return L * (24 * T * C * C + 4 * T * T * C) + 2 * C * V
 
 
+def flops_executed(L, C, T=256, V=67, pruned=True):
+    """What the kernels execute: with last-block pruning the last block runs attention for one
+    query and c_proj + MLP for one token per sequence (its QKV GEMM still covers all tokens)."""
+    f = flops_per_agent_step(L, C, T, V)
+    if pruned:
+        f -= (4 * T * T * C - 4 * T * C) + 18 * C * C * (T - 1)
+    return f
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -244,6 +253,8 @@ def main():
     if rank == 0:
         pk = peaks()
         F = flops_per_agent_step(cfg.n_layer, cfg.n_embd)
+        pruned = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1"
+        Fx = flops_executed(cfg.n_layer, cfg.n_embd, pruned=pruned)
         C, L, T = cfg.n_embd, cfg.n_layer, 256
         rows_per_launch = min(E_gpu * n, 8192) * T           # the engine forwards in chunks of 8192 sequences
         kflops = {"gemm_qkv": 2 * 3 * C * C, "gemm_attn_proj": 2 * C * C, "gemm_fc_gelu": 2 * 4 * C * C,
@@ -267,9 +278,10 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": round(achieved / pk["tflops"], 4), "traffic": None, "peak_source": pk["source"],
-                         "whole_step_tflops": round(value / world * F / 1e12, 1),
-                         "whole_step_frac": round(value / world * F / 1e12 / pk["tflops"], 4),
-                         "flops_per_agent_step": F},
+                         "whole_step_tflops": round(value / world * Fx / 1e12, 1),
+                         "whole_step_frac": round(value / world * Fx / 1e12 / pk["tflops"], 4),
+                         "flops_per_agent_step_executed": Fx, "flops_per_agent_step_reference": F,
+                         "last_block_pruned": pruned},
             "kernels": kern, "phases_ms_last_step": {"observe": phases[0], "forward": phases[1], "sample_step": phases[2]},
             "clocks": clocks,
             "episode_metrics_sum": {"envs": msum[0].item(), "CSR": msum[1].item(), "ISR": msum[2].item(),

@@ -169,6 +169,13 @@ int mg_test_gemm(int device, const void *A_bf16, const void *B_bf16, float *C, i
 int mg_test_attention(int device, const void *q, const void *k, const void *v, void *out,
                       int n_seq, int n_head, int hs);
 
+/* UMMA-rate microbenchmark: average ms per launch of the production GEMM kernel (tile width BN) on dummy operands */
+int mg_test_gemm_time(int device, int M, int N, int K, int BN, int iters, float *ms);
+/* pure UMMA rate: one thread issues iters*4 UMMAs (M128 x N x K16) on smem-resident operands; cycles2 = {issue->done, issue loop} */
+int mg_test_umma_rate(int device, int N, int iters, int ctas, long long *cycles2);
+/* clock64() stamps of the first 4 CTAs of the last fused post-attention launch (profiling aid, out[4][128]) */
+int mg_test_timeline(mg_engine *e, int enable, long long *out);
+
 #ifdef __cplusplus
 }
 #endif

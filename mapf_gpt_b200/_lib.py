@@ -74,6 +74,9 @@ _SIGS = {
     "mg_gen_update_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mg_gen_generate_observations": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_gen_destroy": (None, [C.c_void_p]),
+    "mg_test_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mg_test_gemm_time": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "mg_test_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mg_test_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mg_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
 }

@@ -59,6 +59,8 @@ struct Workspace {
     int chunk_seqs = 0;
     float *X = nullptr;
     __nv_bfloat16 *XN = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr;
+    float *Xc = nullptr;              // compact residual rows of token 255 (last-block pruning)
+    __nv_bfloat16 *ATTc = nullptr;    // compact attention output of token 255
     uint8_t *tok = nullptr;   // staging for forward_tokens
     float *logits = nullptr;
 };
@@ -82,11 +84,13 @@ struct mg_engine {
     int max_episode_steps = 0;
     long long launches = 0;
     bool profiling = false;
+    bool prune_last = true;   // last-block pruning (MAPF_GPT_B200_NO_PRUNE=1 disables it for A/B tests)
     std::vector<EvPair> evs;
     size_t ev_used = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_p[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_total_ms = 0.f, last_phase_ms[3] = {0.f, 0.f, 0.f};
     float kc_ms[KC_COUNT] = {0};
+    long long *d_timeline = nullptr;   // test hook (mg_test_timeline)
     long long kc_n[KC_COUNT] = {0};
 };
 
@@ -191,25 +195,28 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
     return MG_OK;
 }
 
-template <int C>
+template <int C, int NT>
 static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT)
 {
-    constexpr int smem = PostAttnCfg<C>::SMEM_BYTES;
+    using K = PostAttnCfg<C, NT>;
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(post_attn_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
     prof_begin(e, KC_POST);
-    post_attn_kernel<C><<<MT, 320, smem, e->stream>>>(a);
+    post_attn_kernel<C, NT><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
     prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
 }
-static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT)
+static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT, bool single_tiles)
 {
-    if (C == 160) return launch_post_attn_c<160>(e, a, MT);
-    if (C == 256) return launch_post_attn_c<256>(e, a, MT);
+    // NT = 1 (two CTAs per SM) measured faster than NT = 2 (one CTA per SM, shared weight stages): with one CTA per SM
+    // the HBM phases (tile load / store) and the compute phase of an SM do not overlap.  MAPF_GPT_B200_POST_NT=2 selects it.
+    static const int nt_override = getenv("MAPF_GPT_B200_POST_NT") ? atoi(getenv("MAPF_GPT_B200_POST_NT")) : 0;
+    if (C == 160) return (nt_override == 2 && !single_tiles && MT % 2 == 0) ? launch_post_attn_c<160, 2>(e, a, MT) : launch_post_attn_c<160, 1>(e, a, MT);
+    if (C == 256) return launch_post_attn_c<256, 1>(e, a, MT);
     return fail(MG_ERR_ARG, "post_attn: unsupported width %d", C);
 }
 
@@ -234,9 +241,16 @@ template <int EPI>
 static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 {
     if (a.M % 128) return fail(MG_ERR_ARG, "gemm: M=%d not a multiple of 128", a.M);
+    // K == 160: the whole K extent is ONE stage (one barrier wait, ten UMMAs, one commit) -- every stage hand-off costs
+    // the single issuing thread ~300 cycles, more than two N=160 UMMAs take to execute.
+    if (BN == 160 && a.N % 160 == 0 && a.K == 160) return launch_gemm_cfg<160, 160, 1, EPI>(e, a, kc);
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
     if (BN == 256 && a.N % 256 == 0 && a.K % 64 == 0) return launch_gemm_cfg<256, 64, 2, EPI>(e, a, kc);
     if (BN == 128 && a.N % 128 == 0 && a.K % 64 == 0) return launch_gemm_cfg<128, 64, 3, EPI>(e, a, kc);
+    if constexpr (EPI == EPI_STORE_F32) {   // microbenchmark shapes (mg_test_gemm_time)
+        if (BN == 80 && a.N % 80 == 0 && a.K % 64 == 0) return launch_gemm_cfg<80, 64, 4, EPI>(e, a, kc);
+        if (BN == 240 && a.N % 240 == 0 && a.K % 64 == 0) return launch_gemm_cfg<240, 64, 3, EPI>(e, a, kc);
+    }
     return fail(MG_ERR_ARG, "gemm: unsupported shape N=%d K=%d for BN=%d", a.N, a.K, BN);
 }
 static int pick_bn(int C)
@@ -276,14 +290,19 @@ static int ensure_workspace(mg_engine *e, int want_seqs)
     const int C = e->model.cfg.n_embd;
     int chunk = std::min(want_seqs, 8192);
     if (chunk <= w.chunk_seqs) return MG_OK;
-    cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID);
-    w.X = nullptr; w.XN = w.QKV = w.ATT = w.HID = nullptr; w.chunk_seqs = 0;
+    cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc);
+    w.X = w.Xc = nullptr; w.XN = w.QKV = w.ATT = w.HID = w.ATTc = nullptr; w.chunk_seqs = 0;
     const size_t M = (size_t)chunk * 256;
     CU(dalloc(&w.X, M * C));
     CU(dalloc(&w.XN, M * C));
     CU(dalloc(&w.QKV, M * 3 * C));
     CU(dalloc(&w.ATT, M * C));
     CU(dalloc(&w.HID, M * 4 * C));
+    const size_t Mc = ((size_t)chunk + 127) / 128 * 128;
+    CU(dalloc(&w.Xc, Mc * C));
+    CU(dalloc(&w.ATTc, Mc * C));
+    CU(cudaMemsetAsync(w.Xc, 0, Mc * C * 4, e->stream));
+    CU(cudaMemsetAsync(w.ATTc, 0, Mc * C * 2, e->stream));
     w.chunk_seqs = chunk;
     return MG_OK;
 }
@@ -310,17 +329,36 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 GemmArgs g{};
                 g.A = w.XN; g.W = L.wqkv; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
                 if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
+                const bool last = l + 1 == m.cfg.n_layer;
+                if (last && e->prune_last) {
+                    // last block: Q / attention / c_proj / MLP only for token 255 of each sequence (App. D.2)
+                    prof_begin(e, KC_ATTN);
+                    if (hs == 32)
+                        last_attn_kernel<32><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 1.0f / std::sqrt((float)hs));
+                    else
+                        last_attn_kernel<64><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 1.0f / std::sqrt((float)hs));
+                    prof_end(e);
+                    PostAttnArgs pa{};
+                    pa.att = w.ATTc; pa.x = w.Xc; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;
+                    if ((rc = launch_post_attn(e, C, pa, (ns + 127) / 128, true))) return rc;
+                    prof_begin(e, KC_HEAD);
+                    head_compact_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.Xc, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
+                    prof_end(e);
+                    break;
+                }
                 AttnArgs at{};
                 at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
                 at.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
+                at.timeline = e->d_timeline;
                 if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
                 PostAttnArgs pa{};
                 pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;
-                const bool last = l + 1 == m.cfg.n_layer;
                 pa.next_gain = last ? nullptr : m.layers[l + 1].ln1;
                 pa.xn_out = last ? nullptr : w.XN;
-                if ((rc = launch_post_attn(e, C, pa, MT))) return rc;
+                pa.timeline = e->d_timeline;
+                if ((rc = launch_post_attn(e, C, pa, MT, false))) return rc;
             }
+            if (e->prune_last) continue;
             prof_begin(e, KC_HEAD);
             head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.X, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
             prof_end(e);
@@ -397,6 +435,54 @@ static int check_vocab(mg_engine *e)
         CU(cudaMemsetAsync(e->s.vocab_err, 0, 4, e->stream));
         return fail(MG_ERR_VOCAB, "a relative position left the token vocabulary (agents outside the FOV window?)");
     }
+    return MG_OK;
+}
+
+// Pure UMMA issue/execute rate: operands stay in smem (zero-filled), one thread issues `iters` x 4 UMMAs (M128 x N x K16,
+// SS operands, no-swizzle K-major), then commits; out[0] = clock64 cycles from first issue to completion.
+template <int N>
+__global__ void __launch_bounds__(128) umma_rate_kernel(int iters, long long *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *As = smem;                       // 4 k-steps: [8 kc][128][16B] = 16 KB
+    uint8_t *Bs = smem + 16384;               // [8 kc][N][16B]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < (16384 + 8 * N * 16) / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc<256>(&slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+        const uint32_t a = smem_u32(As), b = smem_u32(Bs);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)
+                umma_ss(tmem, umma_desc(a + ks * 4096, 2048, 128), umma_desc(b + ks * 2 * N * 16, N * 16, 128), idesc, 1u);
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<256>(tmem);
+}
+template <int N>
+static int run_umma_rate(int iters, int ctas, long long *d_out, long long *h_out)
+{
+    const int smem = 16384 + 8 * N * 16;
+    CU(cudaFuncSetAttribute(umma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_rate_kernel<N><<<ctas, 128, smem>>>(iters, d_out);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h_out, d_out, 16, cudaMemcpyDeviceToHost));
     return MG_OK;
 }
 
@@ -501,6 +587,7 @@ void mg_engine_destroy(mg_engine *e)
     for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
+    cudaFree(w.Xc); cudaFree(w.ATTc);
     for (auto &p : e->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
@@ -548,6 +635,10 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
     m.layers.resize(cfg->n_layer);
     const char *force_generic = getenv("MAPF_GPT_B200_GENERIC");
     m.fused = (C == 160 || C == 256) && !(force_generic && force_generic[0] == '1');
+    {
+        const char *np = getenv("MAPF_GPT_B200_NO_PRUNE");
+        e->prune_last = !(np && np[0] == '1');
+    }
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;
@@ -939,6 +1030,23 @@ void mg_gen_destroy(mg_gen *g)
 }
 
 // ------------------------------------------------------------------------------------------- test hooks
+// clock64() stamps of the first 4 CTAs of the LAST post_attn launch: out[4][128] (see MG_STAMP ids in fused_kernels.cuh)
+int mg_test_timeline(mg_engine *e, int enable, long long *out)
+{
+    if (!e) return fail(MG_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (enable && !e->d_timeline) {
+        CU(dalloc(&e->d_timeline, 4 * 128));
+        CU(cudaMemset(e->d_timeline, 0, 4 * 128 * 8));
+    }
+    if (out && e->d_timeline) {
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpy(out, e->d_timeline, 4 * 128 * 8, cudaMemcpyDeviceToHost));
+    }
+    if (!enable && e->d_timeline) { cudaFree(e->d_timeline); e->d_timeline = nullptr; }
+    return MG_OK;
+}
+
 int mg_test_gemm(int device, const void *A, const void *B, float *C, int M, int N, int K, int variant)
 {
     CU(cudaSetDevice(device));
@@ -958,6 +1066,51 @@ int mg_test_gemm(int device, const void *A, const void *B, float *C, int M, int 
     cudaFree(At); cudaFree(Bt);
     if (rc) return rc;
     if (err != cudaSuccess) return fail(MG_ERR_CUDA, "test gemm: %s", cudaGetErrorString(err));
+    return MG_OK;
+}
+
+int mg_test_umma_rate(int device, int N, int iters, int ctas, long long *cycles2)
+{
+    CU(cudaSetDevice(device));
+    long long *d = nullptr;
+    CU(dalloc(&d, 2));
+    int rc = MG_ERR_ARG;
+    if (N == 48) rc = run_umma_rate<48>(iters, ctas, d, cycles2);
+    else if (N == 80) rc = run_umma_rate<80>(iters, ctas, d, cycles2);
+    else if (N == 128) rc = run_umma_rate<128>(iters, ctas, d, cycles2);
+    else if (N == 160) rc = run_umma_rate<160>(iters, ctas, d, cycles2);
+    else if (N == 256) rc = run_umma_rate<256>(iters, ctas, d, cycles2);
+    cudaFree(d);
+    return rc;
+}
+
+// UMMA-rate microbenchmark: `iters` launches of the production GEMM on uninitialised tile images; ms = average per launch
+int mg_test_gemm_time(int device, int M, int N, int K, int BN, int iters, float *ms)
+{
+    CU(cudaSetDevice(device));
+    __nv_bfloat16 *At = nullptr, *Bt = nullptr;
+    float *Cd = nullptr;
+    CU(dalloc(&At, (size_t)M * K));
+    CU(dalloc(&Bt, (size_t)N * K));
+    CU(dalloc(&Cd, (size_t)M * N));
+    CU(cudaMemset(At, 0, (size_t)M * K * 2));
+    CU(cudaMemset(Bt, 0, (size_t)N * K * 2));
+    GemmArgs g{};
+    g.A = At; g.W = Bt; g.out = Cd; g.M = M; g.N = N; g.K = K;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = launch_gemm<EPI_STORE_F32>(nullptr, BN, g, 0);
+    if (!rc) {
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters && !rc; i++) rc = launch_gemm<EPI_STORE_F32>(nullptr, BN, g, 0);
+        cudaEventRecord(e1, 0);
+    }
+    cudaError_t err = cudaDeviceSynchronize();
+    if (!rc && err == cudaSuccess) { cudaEventElapsedTime(ms, e0, e1); *ms /= iters; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(At); cudaFree(Bt); cudaFree(Cd);
+    if (rc) return rc;
+    if (err != cudaSuccess) return fail(MG_ERR_CUDA, "gemm_time: %s", cudaGetErrorString(err));
     return MG_OK;
 }
 

@@ -29,7 +29,12 @@ struct PostAttnArgs {
     const float *ln2_gain;         // [C]
     const float *next_gain;        // [C] ln_1 gain of the next block, or nullptr
     __nv_bfloat16 *xn_out;         // A_ti for the next block's QKV GEMM, or nullptr
+    long long *timeline;           // test hook: clock64() stamps of CTA 0..3 ([cta][128]); nullptr in production
 };
+#define MG_STAMP(id)                                                                     \
+    do {                                                                                 \
+        if (a.timeline != nullptr && blockIdx.x < 4) a.timeline[blockIdx.x * 128 + (id)] = clock64(); \
+    } while (0)
 
 // erf-GELU on a PAIR of values with packed fp32x2 math (FFMA2): erf(z) ~ z * P(z^2), odd degree-17 polynomial on
 // |z| <= 3 (z clamped by one saturating FFMA per element), FMA-only, no MUFU.  Max |gelu error| 5e-5 over all x;
@@ -74,78 +79,98 @@ __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean,
     return acc;
 }
 
-template <int C>
+// NT = 128-token tiles per CTA.  NT = 2 (one whole 256-token sequence per CTA, one CTA per SM) lets both tiles share
+// every weight stage: half the L2->SMEM weight traffic per token and more bytes in flight per SM.
+// Timeline measurements (tools/timeline.py, clock64 stamps) drove three choices:
+//   * a weight stage is U k-step units (25.6 KB at C=160) -- every full-barrier wait + fence + commit costs the single
+//     issuing thread ~300 cycles, so 5 KB stages made the issuer, not the tensor pipe, the bottleneck;
+//   * x is pre-loaded into the TMEM accumulator by the workers while the att tile is still in flight, so the c_proj
+//     UMMAs produce x1 = x + proj directly and the first epilogue has no global loads;
+//   * LayerNorm statistics are single-pass (sum, sum of squares) in packed fp32x2.
+template <int C, int NT>
 struct PostAttnCfg {
     static constexpr int HC = C / 2;                 // hidden chunk (FC N, proj2 K per chunk)
     static constexpr int NCH = 4 * C / HC;           // 8 chunks
-    static constexpr int STAGE_BYTES = 32 * C;       // [2 kc][C][16B] == [4 kc][HC][16B]
-    static constexpr int NPROJ = C / 16;             // stages of the proj GEMM (one k-step each)
-    static constexpr int NFC = C / 32;               // stages per FC chunk (two k-steps each)
-    static constexpr int NP2 = HC / 16;              // stages per proj2 chunk (one k-step each)
-    static constexpr int TOTAL_STAGES = NPROJ + NCH * (NFC + NP2);
-    static constexpr int A_BYTES = C * 256;          // [C/8][128][16B]
-    static constexpr int H_BYTES = HC * 256;         // [HC/8][128][16B]
-    static constexpr int STAGES = C <= 160 ? 5 : 8;
-    static constexpr int CTAS_PER_SM = C <= 160 ? 2 : 1;
-    static constexpr uint32_t TMEM_COLS = (C + HC) <= 256 ? 256 : 512;
-    static constexpr int SMEM_BYTES = A_BYTES + 2 * H_BYTES + STAGES * STAGE_BYTES + 4 * 128 * 4 + (2 * STAGES + 12) * 8 + 16;
+    static constexpr int UNIT_BYTES = 32 * C;        // [2 kc][C][16B] == [4 kc][HC][16B]
+    static constexpr int NPROJ = C / 16;             // units of the proj GEMM (one k-step each)
+    static constexpr int NFC = C / 32;               // units per FC chunk (two k-steps each)
+    static constexpr int NP2 = HC / 16;              // units per proj2 chunk (one k-step each)
+    static constexpr int U = C == 160 ? 5 : 4;       // units per stage
+    static constexpr int STAGE_BYTES = U * UNIT_BYTES;
+    static constexpr int TOTAL_STAGES = (NPROJ + NCH * (NFC + NP2)) / U;
+    static constexpr int A_BYTES = C * 256;          // [C/8][128][16B] per tile
+    static constexpr int H_BYTES = HC * 256;         // [HC/8][128][16B] per tile
+    static constexpr int STAGES = NT == 2 ? 4 : (C <= 160 ? 2 : 3);
+    static constexpr int CTAS_PER_SM = (NT == 1 && C <= 160) ? 2 : 1;
+    static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
+    static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
+    static constexpr int THREADS = 64 + 256 * NT;
+    static constexpr int NBAR = 2 * STAGES + 2 + NT * 7;
+    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * STAGE_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
+    static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
+    static_assert(TMEM_COLS <= 512, "post_attn_kernel: TMEM budget");
 };
 
-template <int C>
-__global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_kernel(const PostAttnArgs a)
+template <int C, int NT>
+__global__ void __launch_bounds__(PostAttnCfg<C, NT>::THREADS, PostAttnCfg<C, NT>::CTAS_PER_SM)
+post_attn_kernel(const PostAttnArgs a)
 {
-    using K = PostAttnCfg<C>;
-    constexpr int HC = K::HC, S = K::STAGES;
+    using K = PostAttnCfg<C, NT>;
+    constexpr int HC = K::HC, S = K::STAGES, U = K::U;
+    constexpr int PROD_WARP = 8 * NT, MMA_WARP = 8 * NT + 1;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *As = smem;
-    uint8_t *Hs = As + K::A_BYTES;                       // 2 buffers
-    uint8_t *ring = Hs + 2 * K::H_BYTES;
-    float *red = reinterpret_cast<float *>(ring + S * K::STAGE_BYTES);   // [2 kinds][2 halves][128]
-    uint64_t *full = reinterpret_cast<uint64_t *>(red + 4 * 128);
+    uint8_t *As = smem;                                   // [NT] A tiles
+    uint8_t *Hs = As + NT * K::A_BYTES;                   // [NT] hidden-chunk buffers
+    uint8_t *ring = Hs + NT * K::H_BYTES;
+    float *red = reinterpret_cast<float *>(ring + S * K::STAGE_BYTES);   // [NT][2 kinds][2 halves][128]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + NT * 4 * 128);
     uint64_t *empty = full + S;
-    uint64_t *bar_att = empty + S;       // A tile landed (tx)
-    uint64_t *bar_proj = bar_att + 1;    // proj UMMAs retired
-    uint64_t *bar_ln2 = bar_proj + 1;    // LN2(x1) in smem, x1 in TMEM (256 arrivals)
-    uint64_t *bar_a1f = bar_ln2 + 1;     // FC chunk accumulated
-    uint64_t *bar_a1e = bar_a1f + 1;     // FC chunk drained to registers (256 arrivals)
-    uint64_t *bar_hf = bar_a1e + 1;      // [2] hidden chunk written to smem (256 arrivals)
-    uint64_t *bar_he = bar_hf + 2;       // [2] hidden chunk consumed by proj2 UMMAs
-    uint64_t *bar_done = bar_he + 2;     // all UMMAs retired
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_done + 1);
+    uint64_t *bar_proj = empty + S;      // proj UMMAs retired (all tiles)
+    uint64_t *bar_done = bar_proj + 1;   // all UMMAs retired
+    uint64_t *bar_att = bar_done + 1;    // [NT] A tile landed (tx)
+    uint64_t *bar_x = bar_att + NT;      // [NT] x pre-loaded into the TMEM accumulator (256 arrivals)
+    uint64_t *bar_ln2 = bar_x + NT;      // [NT] LN2(x1) in smem (256 arrivals)
+    uint64_t *bar_a1f = bar_ln2 + NT;    // [NT] FC chunk accumulated
+    uint64_t *bar_a1e = bar_a1f + NT;    // [NT] FC chunk drained to registers (256 arrivals)
+    uint64_t *bar_hf = bar_a1e + NT;     // [NT] hidden chunk written to smem (256 arrivals)
+    uint64_t *bar_he = bar_hf + NT;      // [NT] hidden chunk consumed by the proj2 UMMAs
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_he + NT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.x;
+    const int mt0 = blockIdx.x * NT;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(bar_att, 1);
         mbar_init(bar_proj, 1);
-        mbar_init(bar_ln2, 256);
-        mbar_init(bar_a1f, 1);
-        mbar_init(bar_a1e, 256);
-        mbar_init(&bar_hf[0], 256);
-        mbar_init(&bar_hf[1], 256);
-        mbar_init(&bar_he[0], 1);
-        mbar_init(&bar_he[1], 1);
         mbar_init(bar_done, 1);
+        for (int t = 0; t < NT; t++) {
+            mbar_init(&bar_att[t], 1);
+            mbar_init(&bar_x[t], 256);
+            mbar_init(&bar_ln2[t], 256);
+            mbar_init(&bar_a1f[t], 1);
+            mbar_init(&bar_a1e[t], 256);
+            mbar_init(&bar_hf[t], 256);
+            mbar_init(&bar_he[t], 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc<K::TMEM_COLS>(tmem_slot);
+    if (warp == MMA_WARP) tmem_alloc<K::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == PROD_WARP) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
-            mbar_expect_tx(bar_att, K::A_BYTES);
-            bulk_g2s(As, a.att + (size_t)mt * C * 128, K::A_BYTES, bar_att);
-            bulk_prefetch_l2(a.x + (size_t)mt * C * 128, C * 128 * 4);
+            for (int t = 0; t < NT; t++) {
+                mbar_expect_tx(&bar_att[t], K::A_BYTES);
+                bulk_g2s(As + t * K::A_BYTES, a.att + (size_t)(mt0 + t) * C * 128, K::A_BYTES, &bar_att[t]);
+            }
             const uint8_t *src = reinterpret_cast<const uint8_t *>(a.wstream);
             for (int i = 0; i < K::TOTAL_STAGES; i++) {
                 const int s = i % S;
@@ -154,7 +179,7 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 bulk_g2s(ring + s * K::STAGE_BYTES, src + (size_t)i * K::STAGE_BYTES, K::STAGE_BYTES, &full[s]);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ UMMA issuer
         if (lane == 0) {
             constexpr uint32_t idescC = umma_idesc_bf16(128, C, 0, 0);
@@ -167,43 +192,68 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 tc_fence_after();
                 return r_addr + s * K::STAGE_BYTES;
             };
-            // proj: acc_main = att @ Wproj^T
-            mbar_wait(bar_att, 0);
+            // proj: acc_main (pre-loaded with x) += att @ Wproj^T
+            MG_STAMP(0);
+            for (int t = 0; t < NT; t++) {
+                mbar_wait(&bar_att[t], 0);
+                mbar_wait(&bar_x[t], 0);
+            }
             tc_fence_after();
-            for (int ks = 0; ks < K::NPROJ; ks++, i++) {
+            MG_STAMP(1);
+            for (int st = 0; st < K::NPROJ / U; st++, i++) {
                 const uint32_t b = stage_wait(i);
-                umma_ss(tmem, umma_desc(a_addr + ks * 4096, 2048, 128), umma_desc(b, C * 16, 128), idescC, ks != 0);
+#pragma unroll
+                for (int t = 0; t < NT; t++)
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
+                                umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
                 umma_commit(&empty[i % S]);
             }
             umma_commit(bar_proj);
-            mbar_wait(bar_ln2, 0);
-            tc_fence_after();
+            MG_STAMP(2);
             auto fc = [&](int j) {
-                if (j > 0) {
-                    mbar_wait(bar_a1e, (j - 1) & 1);
-                    tc_fence_after();
-                }
-                for (int kb = 0; kb < K::NFC; kb++, i++) {
+                for (int st = 0; st < K::NFC / U; st++, i++) {
                     const uint32_t b = stage_wait(i);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ks++)
-                        umma_ss(tmem + C, umma_desc(a_addr + (kb * 2 + ks) * 4096, 2048, 128),
-                                umma_desc(b + ks * 2 * (HC * 16), HC * 16, 128), idescH, (kb | ks) != 0);
+                    for (int t = 0; t < NT; t++) {
+                        if (st == 0) {
+                            if (j == 0) mbar_wait(&bar_ln2[t], 0);
+                            else mbar_wait(&bar_a1e[t], (j - 1) & 1);
+                            tc_fence_after();
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; u++)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ks++)
+                                umma_ss(tmem + t * K::TILE_COLS + C,
+                                        umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
+                                        umma_desc(b + u * K::UNIT_BYTES + ks * 2 * (HC * 16), HC * 16, 128), idescH,
+                                        (st | u | ks) != 0);
+                        if (st == K::NFC / U - 1) umma_commit(&bar_a1f[t]);
+                    }
                     umma_commit(&empty[i % S]);
                 }
-                umma_commit(bar_a1f);
+                MG_STAMP(10 + 2 * j);
             };
             auto p2 = [&](int j) {
-                const int hb = j & 1;
-                mbar_wait(&bar_hf[hb], (j >> 1) & 1);
-                tc_fence_after();
-                for (int ks = 0; ks < K::NP2; ks++, i++) {
+                for (int st = 0; st < K::NP2 / U; st++, i++) {
                     const uint32_t b = stage_wait(i);
-                    umma_ss(tmem, umma_desc(h_addr + hb * K::H_BYTES + ks * 4096, 2048, 128), umma_desc(b, C * 16, 128),
-                            idescC, 1u);
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        if (st == 0) {
+                            mbar_wait(&bar_hf[t], j & 1);
+                            tc_fence_after();
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; u++)
+                            umma_ss(tmem + t * K::TILE_COLS, umma_desc(h_addr + t * K::H_BYTES + (st * U + u) * 4096, 2048, 128),
+                                    umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
+                        if (st == K::NP2 / U - 1) umma_commit(&bar_he[t]);
+                    }
                     umma_commit(&empty[i % S]);
                 }
-                umma_commit(&bar_he[hb]);
+                MG_STAMP(11 + 2 * j);
             };
             fc(0);
             for (int j = 0; j < K::NCH; j++) {
@@ -211,66 +261,73 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 p2(j);
             }
             umma_commit(bar_done);
+            MG_STAMP(40);
         }
     } else {
-        // ------------------------------------------------------------------ workers (256 threads)
-        const int q = warp & 3, h = warp >> 2;
+        // ------------------------------------------------------------------ workers (256 threads per tile)
+        const int t = warp >> 3;                          // tile of this worker
+        const int q = warp & 3, h = (warp >> 2) & 1;
         const int r = q * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const int mt = mt0 + t;
+        const uint32_t trow = tmem + t * K::TILE_COLS + ((uint32_t)(q * 32) << 16);
+        uint8_t *At = As + t * K::A_BYTES;
         constexpr int HALF = C / 2;                       // columns of the residual handled by this thread
-        float *red_s = red, *red_q = red + 256;
+        float *red_s = red + t * 512, *red_q = red_s + 256;
         const float inv_c = 1.0f / (float)C;
+        const uint32_t nb = 1 + t;                        // named barrier of this tile's 256 workers
+        float4 *Xg = reinterpret_cast<float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
 
-        // ---- epilogue 1: x1 = x + proj, LN2 -> A tile, x1 -> TMEM
-        mbar_wait(bar_proj, 0);
-        tc_fence_after();
+        // ---- x -> TMEM accumulator (overlaps the att tile load); c_proj then accumulates onto it.
+        // All loads are issued before the first TMEM store so the thread pays ONE memory round trip.
         {
-            const float4 *Xg = reinterpret_cast<const float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
-            float sum = 0.f;
-            f32x2 sum2 = pk2(0.f, 0.f);
-#pragma unroll 1
-            for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + c0, v);
-                float4 xv[4];
+            float4 xv[HALF / 4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) xv[j] = Xg[(size_t)(c0 / 4 + j) * 128];
-                tmem_wait_ld();
+            for (int j = 0; j < HALF / 4; j++) xv[j] = Xg[(size_t)(h * (HALF / 4) + j) * 128];
+#pragma unroll
+            for (int i = 0; i < HALF / 16; i++) {
+                uint32_t v[16];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const f32x2 e0 = add2(pk2u(v[4 * j + 0], v[4 * j + 1]), pk2(xv[j].x, xv[j].y));
-                    const f32x2 e1 = add2(pk2u(v[4 * j + 2], v[4 * j + 3]), pk2(xv[j].z, xv[j].w));
-                    upk2u(e0, v[4 * j + 0], v[4 * j + 1]);
-                    upk2u(e1, v[4 * j + 2], v[4 * j + 3]);
-                    sum2 = add2(sum2, add2(e0, e1));
+                    v[4 * j + 0] = __float_as_uint(xv[4 * i + j].x); v[4 * j + 1] = __float_as_uint(xv[4 * i + j].y);
+                    v[4 * j + 2] = __float_as_uint(xv[4 * i + j].z); v[4 * j + 3] = __float_as_uint(xv[4 * i + j].w);
                 }
-                tmem_st16(trow + c0, v);
+                tmem_st16(trow + h * HALF + 16 * i, v);
             }
-            tmem_wait_st();
-            {
-                float s0, s1;
-                upk2(sum2, s0, s1);
-                sum = s0 + s1;
-            }
-            red_s[h * 128 + r] = sum;
-            named_bar_sync(1, 256);
-            const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
-            f32x2 sq2 = pk2(0.f, 0.f);
-            const f32x2 negmean = pk2(-mean, -mean);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bar_x[t]);
+
+        // ---- epilogue 1: LN2(x1) -> A tile (x1 = x + proj stays in TMEM)
+        mbar_wait(bar_proj, 0);
+        tc_fence_after();
+        if (threadIdx.x == 0) MG_STAMP(50);
+        {
+            f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
 #pragma unroll 1
             for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(trow + c0, v);
                 tmem_wait_ld();
-                sq2 = sqdev16(v, negmean, sq2);
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const f32x2 e = pk2u(v[j], v[j + 1]);
+                    sum2 = add2(sum2, e);
+                    sq2 = fma2(e, e, sq2);
+                }
             }
+            if (threadIdx.x == 0) MG_STAMP(51);
             {
-                float s0, s1;
-                upk2(sq2, s0, s1);
-                red_q[h * 128 + r] = s0 + s1;
+                float s0, s1, q0, q1;
+                upk2(sum2, s0, s1);
+                upk2(sq2, q0, q1);
+                red_s[h * 128 + r] = s0 + s1;
+                red_q[h * 128 + r] = q0 + q1;
             }
-            named_bar_sync(1, 256);
-            const float rstd = rsqrtf((red_q[r] + red_q[128 + r]) * inv_c + 1e-5f);
+            named_bar_sync(nb, 256);
+            const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
+            const float var = fmaxf((red_q[r] + red_q[128 + r]) * inv_c - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + 1e-5f);
             const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
             const float4 *g4 = reinterpret_cast<const float4 *>(a.ln2_gain);
 #pragma unroll 1
@@ -280,49 +337,53 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 2; j++)
-                    *reinterpret_cast<uint4 *>(As + ((c0 / 8 + j) * 128 + r) * 16) =
+                    *reinterpret_cast<uint4 *>(At + ((c0 / 8 + j) * 128 + r) * 16) =
                         ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
             }
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(bar_ln2);
+            mbar_arrive(&bar_ln2[t]);
+            if (threadIdx.x == 0) MG_STAMP(52);
         }
 
         // ---- MLP chunks: acc1 -> GELU -> hidden chunk in smem
         constexpr int HH = HC / 2;            // hidden columns per thread per chunk
         constexpr int NV = HH / 8;            // 16-byte groups
+        uint8_t *Hb = Hs + t * K::H_BYTES;
 #pragma unroll 1
         for (int j = 0; j < K::NCH; j++) {
-            const int hb = j & 1;
-            mbar_wait(bar_a1f, j & 1);
+            mbar_wait(&bar_a1f[t], j & 1);
             tc_fence_after();
+            if (threadIdx.x == 0) MG_STAMP(60 + 3 * j);
             uint32_t v[NV][8];
 #pragma unroll
             for (int g = 0; g < NV; g++) tmem_ld8(trow + C + h * HH + g * 8, v[g]);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(bar_a1e);
-            if (j >= 2) mbar_wait(&bar_he[hb], ((j >> 1) - 1) & 1);
-            uint8_t *Hb = Hs + hb * K::H_BYTES;
+            mbar_arrive(&bar_a1e[t]);
+            if (threadIdx.x == 0) MG_STAMP(61 + 3 * j);
+            uint4 o[NV];
 #pragma unroll
             for (int g = 0; g < NV; g++) {
-                uint4 o;
-                o.x = pack_bf16x2_p(gelu2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1])));
-                o.y = pack_bf16x2_p(gelu2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3])));
-                o.z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
-                o.w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
-                *reinterpret_cast<uint4 *>(Hb + ((h * NV + g) * 128 + r) * 16) = o;
+                o[g].x = pack_bf16x2_p(gelu2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1])));
+                o[g].y = pack_bf16x2_p(gelu2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3])));
+                o[g].z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
+                o[g].w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
             }
+            if (j >= 1) mbar_wait(&bar_he[t], (j - 1) & 1);       // proj2(j-1) has finished reading the buffer
+#pragma unroll
+            for (int g = 0; g < NV; g++) *reinterpret_cast<uint4 *>(Hb + ((h * NV + g) * 128 + r) * 16) = o[g];
             fence_proxy_async_smem();
-            mbar_arrive(&bar_hf[hb]);
+            mbar_arrive(&bar_hf[t]);
+            if (threadIdx.x == 0) MG_STAMP(62 + 3 * j);
         }
 
         // ---- final epilogue: x' -> HBM, xn = LN1_next(x') -> HBM
         mbar_wait(bar_done, 0);
         tc_fence_after();
+        if (threadIdx.x == 0) MG_STAMP(90);
         {
-            float4 *Xg = reinterpret_cast<float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
-            float sum = 0.f;
+            f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
 #pragma unroll 1
             for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
                 uint32_t v[16];
@@ -330,32 +391,26 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float4 o = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
-                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    Xg[(size_t)(c0 / 4 + j) * 128] = o;
-                    sum += (o.x + o.y) + (o.z + o.w);
+                    Xg[(size_t)(c0 / 4 + j) * 128] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
+                                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    const f32x2 e0 = pk2u(v[4 * j + 0], v[4 * j + 1]), e1 = pk2u(v[4 * j + 2], v[4 * j + 3]);
+                    sum2 = add2(sum2, add2(e0, e1));
+                    sq2 = fma2(e0, e0, sq2);
+                    sq2 = fma2(e1, e1, sq2);
                 }
             }
             if (a.xn_out != nullptr) {
-                red_s[h * 128 + r] = sum;
-                named_bar_sync(1, 256);
-                const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
-                f32x2 sq2 = pk2(0.f, 0.f);
-                const f32x2 negmean = pk2(-mean, -mean);
-#pragma unroll 1
-                for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(trow + c0, v);
-                    tmem_wait_ld();
-                    sq2 = sqdev16(v, negmean, sq2);
-                }
                 {
-                    float s0, s1;
-                    upk2(sq2, s0, s1);
-                    red_q[h * 128 + r] = s0 + s1;
+                    float s0, s1, q0, q1;
+                    upk2(sum2, s0, s1);
+                    upk2(sq2, q0, q1);
+                    red_s[h * 128 + r] = s0 + s1;
+                    red_q[h * 128 + r] = q0 + q1;
                 }
-                named_bar_sync(1, 256);
-                const float rstd = rsqrtf((red_q[r] + red_q[128 + r]) * inv_c + 1e-5f);
+                named_bar_sync(nb, 256);
+                const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
+                const float var = fmaxf((red_q[r] + red_q[128 + r]) * inv_c - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
                 const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
                 const float4 *g4 = reinterpret_cast<const float4 *>(a.next_gain);
                 uint4 *O = reinterpret_cast<uint4 *>(a.xn_out) + (size_t)mt * (C / 8) * 128 + r;
@@ -372,9 +427,10 @@ __global__ void __launch_bounds__(320, PostAttnCfg<C>::CTAS_PER_SM) post_attn_ke
             }
         }
     }
+    if (threadIdx.x == 0) MG_STAMP(91);
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc<K::TMEM_COLS>(tmem);
+    if (warp == MMA_WARP) tmem_dealloc<K::TMEM_COLS>(tmem);
 }
 
 // embedding + ln_1 of block 0 in one pass (model.py:171-175 + model.py:102): X_ti and A_ti out.
@@ -423,6 +479,148 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(const uint8_t *__restrict
         o.z = pack_bf16x2((t1.x + p1.x - mean) * rstd * g1.x, (t1.y + p1.y - mean) * rstd * g1.y);
         o.w = pack_bf16x2((t1.z + p1.z - mean) * rstd * g1.z, (t1.w + p1.w - mean) * rstd * g1.w);
         O[(size_t)c8 * 128] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Last block pruning: only logits[255][0:5] are consumed (model.py:186,249-252), so in the LAST
+// block K and V are needed for all 256 tokens but Q, attention output, c_proj and the MLP only for token 255.
+// last_attn_kernel: one warp per (sequence, head) on CUDA cores (1 query x 256 keys x hs): softmax(q K^T / sqrt(hs)) V,
+// written into a COMPACT A tile image (row = sequence), and the residual row of token 255 gathered next to it.
+// post_attn_kernel then runs on n_seq rows instead of 256 * n_seq.
+// ------------------------------------------------------------------------------------------------
+template <int HS>
+__global__ void __launch_bounds__(512) last_attn_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ X,
+                                                        __nv_bfloat16 *__restrict__ att_c, float *__restrict__ x_c, int n_head,
+                                                        int C, float scale)
+{
+    const int seq = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mtc = seq >> 7, rc = seq & 127;
+    // gather x[seq*256 + 255] -> compact row
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(X) + (size_t)(seq * 2 + 1) * (C / 4) * 128 + 127;
+        float4 *dst = reinterpret_cast<float4 *>(x_c) + (size_t)mtc * (C / 4) * 128 + rc;
+        for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) dst[(size_t)c4 * 128] = src[(size_t)c4 * 128];
+    }
+    if (head >= n_head) return;
+    const size_t blk = (size_t)(HS / 8) * 256 * 8;
+    const __nv_bfloat16 *Qg = qkv + (((size_t)seq * 3 + 0) * n_head + head) * blk;
+    const uint4 *Kg = reinterpret_cast<const uint4 *>(qkv + (((size_t)seq * 3 + 1) * n_head + head) * blk);
+    const __nv_bfloat16 *Vg = qkv + (((size_t)seq * 3 + 2) * n_head + head) * blk;
+    float q[HS];
+#pragma unroll
+    for (int c = 0; c < HS / 8; c++) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(Qg + ((size_t)c * 256 + 255) * 8);
+        const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            q[8 * c + 2 * j] = f.x; q[8 * c + 2 * j + 1] = f.y;
+        }
+    }
+    float s[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int key = lane + 32 * i;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < HS / 8; c++) {
+            const uint4 u = Kg[(size_t)c * 256 + key];
+            const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                acc = fmaf(q[8 * c + 2 * j], f.x, acc);
+                acc = fmaf(q[8 * c + 2 * j + 1], f.y, acc);
+            }
+        }
+        s[i] = acc * scale;
+        mx = fmaxf(mx, s[i]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        s[i] = __expf(s[i] - mx);
+        sum += s[i];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    // o[d] = sum_j p_j v[j][d]: lane owns d = lane (+32 for hs 64); p_j broadcast from its owner lane
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll 8
+        for (int l = 0; l < 32; l++) {
+            const float p = __shfl_sync(0xffffffffu, s[i], l);
+            const int key = l + 32 * i;
+            o0 = fmaf(p, __bfloat162float(Vg[((size_t)(lane >> 3) * 256 + key) * 8 + (lane & 7)]), o0);
+            if (HS == 64) o1 = fmaf(p, __bfloat162float(Vg[((size_t)((lane + 32) >> 3) * 256 + key) * 8 + (lane & 7)]), o1);
+        }
+    }
+    __nv_bfloat16 *dst = att_c + (size_t)mtc * C * 128;
+    {
+        const int col = head * HS + lane;
+        dst[((size_t)(col >> 3) * 128 + rc) * 8 + (col & 7)] = __float2bfloat16(o0 * inv);
+        if (HS == 64) {
+            const int col1 = col + 32;
+            dst[((size_t)(col1 >> 3) * 128 + rc) * 8 + (col1 & 7)] = __float2bfloat16(o1 * inv);
+        }
+    }
+}
+
+// head on the compact residual (row = sequence): ln_f + 5 logits
+__global__ void __launch_bounds__(128) head_compact_kernel(const float *__restrict__ Xc, const float *__restrict__ gain,
+                                                           const float *__restrict__ wte, float *__restrict__ logits, int C,
+                                                           int n_seq)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seq = blockIdx.x * 4 + warp;
+    if (seq >= n_seq) return;
+    const float4 *Xi = reinterpret_cast<const float4 *>(Xc) + (size_t)(seq >> 7) * (C / 4) * 128 + (seq & 127);
+    float s = 0.f;
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 v = Xi[(size_t)c4 * 128];
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 v = Xi[(size_t)c4 * 128];
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + 1e-5f);
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 v = Xi[(size_t)c4 * 128];
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gain) + c4);
+        const float y0 = (v.x - mean) * rstd * g.x, y1 = (v.y - mean) * rstd * g.y;
+        const float y2 = (v.z - mean) * rstd * g.z, y3 = (v.w - mean) * rstd * g.w;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(wte + (size_t)k * C) + c4);
+            acc[k] += y0 * w.x + y1 * w.y + y2 * w.z + y3 * w.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane < 5) {
+        float v = acc[0];
+        if (lane == 1) v = acc[1];
+        if (lane == 2) v = acc[2];
+        if (lane == 3) v = acc[3];
+        if (lane == 4) v = acc[4];
+        logits[(size_t)seq * 8 + lane] = v;
     }
 }
 

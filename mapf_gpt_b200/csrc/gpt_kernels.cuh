@@ -185,7 +185,12 @@ struct AttnArgs {
     int n_head, C;
     float scale_log2e;         // (1/sqrt(hs)) * log2(e)
     int dbg_variant;
+    long long *timeline;       // test hook: clock64() stamps of CTA 0..3 ([cta][128], ids 100..); nullptr in production
 };
+#define MG_ASTAMP(id)                                                                    \
+    do {                                                                                 \
+        if (a.timeline != nullptr && blockIdx.x < 4) a.timeline[blockIdx.x * 128 + (id)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
             const __nv_bfloat16 *Qg = a.qkv + (((size_t)seq * 3 + 0) * a.n_head + head) * blk;
             const __nv_bfloat16 *Kg = a.qkv + (((size_t)seq * 3 + 1) * a.n_head + head) * blk;
             const __nv_bfloat16 *Vg = a.qkv + (((size_t)seq * 3 + 2) * a.n_head + head) * blk;
+            MG_ASTAMP(100);
             mbar_expect_tx(&bars[0], Q_BYTES + K_BYTES);
 #pragma unroll
             for (int c = 0; c < HS / 8; c++)
@@ -257,6 +263,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
             // S = Q K^T
             mbar_wait(&bars[0], 0);
             tc_fence_after();
+            MG_ASTAMP(101);
             {
                 constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
                 const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
@@ -270,6 +277,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
             mbar_wait(&bars[3], 0);
             mbar_wait(&bars[1], 0);
             tc_fence_after();
+            MG_ASTAMP(102);
             {
                 constexpr uint32_t idesc = umma_idesc_bf16(128, HS + 16, 0, 1);
                 const uint32_t pa = smem_u32(Ps), va = smem_u32(Vs);
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
                     umma_ss(tmem, umma_desc(pa + ks * 2 * 2048, 2048, 128), umma_desc(va + ks * 2 * 128, 128, 4096), idesc,
                             ks != 0 ? 1u : 0u);
                 umma_commit(&bars[4]);
+                MG_ASTAMP(103);
             }
         }
     } else {
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         mbar_wait(&bars[2], 0);
         tc_fence_after();
+        if (threadIdx.x == 0) MG_ASTAMP(110);
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
 #pragma unroll
             for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
         }
+        if (threadIdx.x == 0) MG_ASTAMP(111);
         redm[kh * 128 + r] = mx;
         named_bar_sync(1, 256);
         mx = fmaxf(redm[r], redm[128 + r]);
@@ -321,9 +332,11 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(&bars[3]);
+        if (threadIdx.x == 0) MG_ASTAMP(112);
 
         mbar_wait(&bars[4], 0);
         tc_fence_after();
+        if (threadIdx.x == 0) MG_ASTAMP(113);
         uint32_t sv[8];
         tmem_ld8(trow + HS, sv);               // row sum (all 16 extra columns hold it)
         constexpr int DH = HS / 2;             // output columns per thread
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
             *O = o;
         }
     }
+    if (threadIdx.x == 0) MG_ASTAMP(114);
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc<256>(tmem);
