@@ -39,7 +39,7 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 // ------------------------------------------------------------------------------------------- model
-enum KernelClass { KC_BFS = 0, KC_OBSERVE, KC_EMBED, KC_LN, KC_QKV, KC_ATTN, KC_PROJ, KC_FC, KC_PROJ2, KC_HEAD, KC_STEP, KC_POST, KC_COUNT };
+enum KernelClass { KC_BFS = 0, KC_OBSERVE, KC_EMBED, KC_LN, KC_QKV, KC_ATTN, KC_PROJ, KC_FC, KC_PROJ2, KC_HEAD, KC_STEP, KC_POST, KC_ATTN_LAST, KC_POST_LAST, KC_COUNT };
 
 struct Layer {
     float *ln1 = nullptr, *ln2 = nullptr;
@@ -196,7 +196,7 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
 }
 
 template <int C, int NT>
-static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT)
+static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT, int kc)
 {
     using K = PostAttnCfg<C, NT>;
     static bool attr_set = false;
@@ -204,7 +204,7 @@ static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT)
         CU(cudaFuncSetAttribute(post_attn_kernel<C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
-    prof_begin(e, KC_POST);
+    prof_begin(e, kc);
     post_attn_kernel<C, NT><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
     prof_end(e);
     CU(cudaGetLastError());
@@ -215,8 +215,11 @@ static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT, 
     // NT = 1 (two CTAs per SM) measured faster than NT = 2 (one CTA per SM, shared weight stages): with one CTA per SM
     // the HBM phases (tile load / store) and the compute phase of an SM do not overlap.  MAPF_GPT_B200_POST_NT=2 selects it.
     static const int nt_override = getenv("MAPF_GPT_B200_POST_NT") ? atoi(getenv("MAPF_GPT_B200_POST_NT")) : 0;
-    if (C == 160) return (nt_override == 2 && !single_tiles && MT % 2 == 0) ? launch_post_attn_c<160, 2>(e, a, MT) : launch_post_attn_c<160, 1>(e, a, MT);
-    if (C == 256) return launch_post_attn_c<256, 1>(e, a, MT);
+    const int kc = single_tiles ? KC_POST_LAST : KC_POST;
+    if (C == 160)
+        return (nt_override == 2 && !single_tiles && MT % 2 == 0) ? launch_post_attn_c<160, 2>(e, a, MT, kc)
+                                                                  : launch_post_attn_c<160, 1>(e, a, MT, kc);
+    if (C == 256) return launch_post_attn_c<256, 1>(e, a, MT, kc);
     return fail(MG_ERR_ARG, "post_attn: unsupported width %d", C);
 }
 
@@ -241,9 +244,7 @@ template <int EPI>
 static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 {
     if (a.M % 128) return fail(MG_ERR_ARG, "gemm: M=%d not a multiple of 128", a.M);
-    // K == 160: the whole K extent is ONE stage (one barrier wait, ten UMMAs, one commit) -- every stage hand-off costs
-    // the single issuing thread ~300 cycles, more than two N=160 UMMAs take to execute.
-    if (BN == 160 && a.N % 160 == 0 && a.K == 160) return launch_gemm_cfg<160, 160, 1, EPI>(e, a, kc);
+    // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
     if (BN == 256 && a.N % 256 == 0 && a.K % 64 == 0) return launch_gemm_cfg<256, 64, 2, EPI>(e, a, kc);
     if (BN == 128 && a.N % 128 == 0 && a.K % 64 == 0) return launch_gemm_cfg<128, 64, 3, EPI>(e, a, kc);
@@ -271,7 +272,7 @@ static int launch_attn_hs(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream
         attr_set = true;
     }
     if (e) prof_begin(e, KC_ATTN);
-    attn_kernel<HS><<<n_seq * a.n_head * 2, 288, smem, st>>>(a);
+    attn_kernel<HS><<<n_seq * a.n_head, 288, smem, st>>>(a);
     if (e) prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
@@ -332,7 +333,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 const bool last = l + 1 == m.cfg.n_layer;
                 if (last && e->prune_last) {
                     // last block: Q / attention / c_proj / MLP only for token 255 of each sequence (App. D.2)
-                    prof_begin(e, KC_ATTN);
+                    prof_begin(e, KC_ATTN_LAST);
                     if (hs == 32)
                         last_attn_kernel<32><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 1.0f / std::sqrt((float)hs));
                     else

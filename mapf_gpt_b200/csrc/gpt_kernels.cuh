@@ -206,6 +206,8 @@ __device__ __forceinline__ float max3(float a, float b, float c)
     return r;
 }
 
+// One CTA per (sequence, head): K and V are loaded once and both 128-query tiles run back to back (the second Q tile
+// is fetched while the first one is in its softmax).
 // warps 0-7: softmax (thread pair per query row: TMEM lane quadrant = warp&3, key half = warp>>2) + epilogue,
 // warp 8: bulk copies + UMMA issue.  V carries 16 extra columns of ones so that the P V UMMA also produces the
 // row sum of the (bf16-rounded) probabilities in TMEM column HS -- no per-element add in the softmax loop.
@@ -215,21 +217,23 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
     constexpr int Q_BYTES = 128 * HS * 2, K_BYTES = 256 * HS * 2, V_BYTES = 256 * (HS + 16) * 2, P_BYTES = 128 * 256 * 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *Qs = smem, *Ks = Qs + Q_BYTES, *Vs = Ks + K_BYTES, *Ps = Vs + V_BYTES;
-    float *redm = reinterpret_cast<float *>(Qs);                    // [2][128]; Q is dead once S = Q K^T has retired
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Ps + P_BYTES);    // QK, V, S, P, O
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+    float *redm = reinterpret_cast<float *>(Ps + P_BYTES - 1024);   // [2][128] row-max exchange, aliased on the P tail
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Ps + P_BYTES);
+    uint64_t *bK = bars, *bQ1 = bars + 1, *bV = bars + 2, *bS = bars + 3, *bP = bars + 4, *bO = bars + 5, *bE = bars + 6;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x & 1;
-    const int head = (blockIdx.x >> 1) % a.n_head;
-    const int seq = (blockIdx.x >> 1) / a.n_head;
+    const int head = blockIdx.x % a.n_head;
+    const int seq = blockIdx.x / a.n_head;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], 1);
-        mbar_init(&bars[3], 256);
-        mbar_init(&bars[4], 1);
+        mbar_init(bK, 1);
+        mbar_init(bQ1, 1);
+        mbar_init(bV, 1);
+        mbar_init(bS, 1);
+        mbar_init(bP, 256);
+        mbar_init(bO, 1);
+        mbar_init(bE, 256);
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc<256>(tmem_slot);
@@ -252,125 +256,137 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
             const __nv_bfloat16 *Kg = a.qkv + (((size_t)seq * 3 + 1) * a.n_head + head) * blk;
             const __nv_bfloat16 *Vg = a.qkv + (((size_t)seq * 3 + 2) * a.n_head + head) * blk;
             MG_ASTAMP(100);
-            mbar_expect_tx(&bars[0], Q_BYTES + K_BYTES);
+            mbar_expect_tx(bK, Q_BYTES + K_BYTES);
 #pragma unroll
-            for (int c = 0; c < HS / 8; c++)
-                bulk_g2s(Qs + c * 2048, Qg + ((size_t)c * 256 + qt * 128) * 8, 2048, &bars[0]);
-            bulk_g2s(Ks, Kg, K_BYTES, &bars[0]);
-            mbar_expect_tx(&bars[1], K_BYTES);
-            bulk_g2s(Vs, Vg, K_BYTES, &bars[1]);
-
-            // S = Q K^T
-            mbar_wait(&bars[0], 0);
-            tc_fence_after();
-            MG_ASTAMP(101);
-            {
-                constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
-                const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
+            for (int c = 0; c < HS / 8; c++) bulk_g2s(Qs + c * 2048, Qg + ((size_t)c * 256) * 8, 2048, bK);
+            bulk_g2s(Ks, Kg, K_BYTES, bK);
+            mbar_expect_tx(bV, K_BYTES);
+            bulk_g2s(Vs, Vg, K_BYTES, bV);
+            constexpr uint32_t idescS = umma_idesc_bf16(128, 256, 0, 0);
+            constexpr uint32_t idescO = umma_idesc_bf16(128, HS + 16, 0, 1);
+            const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks), pa = smem_u32(Ps), va = smem_u32(Vs);
+#pragma unroll 1
+            for (int qt = 0; qt < 2; qt++) {
+                // S = Q K^T
+                if (qt == 0) mbar_wait(bK, 0);
+                else {
+                    mbar_wait(bE, 0);       // epilogue of tile 0 has drained O from TMEM
+                    mbar_wait(bQ1, 0);
+                }
+                tc_fence_after();
+                if (qt == 0) MG_ASTAMP(101);
 #pragma unroll
                 for (int ks = 0; ks < HS / 16; ks++)
-                    umma_ss(tmem, umma_desc(qa + ks * 2 * 2048, 2048, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128), idesc,
+                    umma_ss(tmem, umma_desc(qa + ks * 2 * 2048, 2048, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128), idescS,
                             ks != 0 ? 1u : 0u);
-                umma_commit(&bars[2]);
-            }
-            // [O | rowsum] = P [V | 1]   (B MN-major: 16 B = 8 d of one key; keys 16 B apart; d-chunks 4096 B apart)
-            mbar_wait(&bars[3], 0);
-            mbar_wait(&bars[1], 0);
-            tc_fence_after();
-            MG_ASTAMP(102);
-            {
-                constexpr uint32_t idesc = umma_idesc_bf16(128, HS + 16, 0, 1);
-                const uint32_t pa = smem_u32(Ps), va = smem_u32(Vs);
+                umma_commit(bS);
+                if (qt == 0) {              // Q smem is free once S(0) has retired: fetch the second query tile
+                    mbar_wait(bS, 0);
+                    mbar_expect_tx(bQ1, Q_BYTES);
+#pragma unroll
+                    for (int c = 0; c < HS / 8; c++) bulk_g2s(Qs + c * 2048, Qg + ((size_t)c * 256 + 128) * 8, 2048, bQ1);
+                }
+                // [O | rowsum] = P [V | 1]   (B MN-major: 16 B = 8 d of one key; keys 16 B apart; d-chunks 4096 B apart)
+                mbar_wait(bP, qt);
+                if (qt == 0) mbar_wait(bV, 0);
+                tc_fence_after();
+                if (qt == 0) MG_ASTAMP(102);
 #pragma unroll
                 for (int ks = 0; ks < 16; ks++)
-                    umma_ss(tmem, umma_desc(pa + ks * 2 * 2048, 2048, 128), umma_desc(va + ks * 2 * 128, 128, 4096), idesc,
+                    umma_ss(tmem, umma_desc(pa + ks * 2 * 2048, 2048, 128), umma_desc(va + ks * 2 * 128, 128, 4096), idescO,
                             ks != 0 ? 1u : 0u);
-                umma_commit(&bars[4]);
-                MG_ASTAMP(103);
+                umma_commit(bO);
+                if (qt == 0) MG_ASTAMP(103);
             }
         }
     } else {
         const int q = warp & 3, kh = warp >> 2;
         const int r = q * 32 + lane;  // query row within the tile
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-        mbar_wait(&bars[2], 0);
-        tc_fence_after();
-        if (threadIdx.x == 0) MG_ASTAMP(110);
-        float mx = -INFINITY;
+        const f32x2 sc2 = pk2(a.scale_log2e, a.scale_log2e);
 #pragma unroll 1
-        for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(trow + c0, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-        }
-        if (threadIdx.x == 0) MG_ASTAMP(111);
-        redm[kh * 128 + r] = mx;
-        named_bar_sync(1, 256);
-        mx = fmaxf(redm[r], redm[128 + r]);
-        const float moff = mx * a.scale_log2e;
-        const f32x2 sc2 = pk2(a.scale_log2e, a.scale_log2e), mo2 = pk2(-moff, -moff);
+        for (int qt = 0; qt < 2; qt++) {
+            mbar_wait(bS, qt);
+            tc_fence_after();
+            if (threadIdx.x == 0 && qt == 0) MG_ASTAMP(110);
+            float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(trow + c0, v);
-            tmem_wait_ld();
+            for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c0, v);
+                tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t w[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    float e0, e1;
-                    upk2(fma2(pk2u(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), sc2, mo2), e0, e1);   // one FFMA2 per two scores
-                    w[t] = pack_bf16x2(ex2_approx(e0), ex2_approx(e1));
-                }
-                const uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4 *>(Ps + ((c0 / 8 + j) * 128 + r) * 16) = o;
+                for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             }
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(&bars[3]);
-        if (threadIdx.x == 0) MG_ASTAMP(112);
+            if (threadIdx.x == 0 && qt == 0) MG_ASTAMP(111);
+            redm[kh * 128 + r] = mx;
+            named_bar_sync(1, 256);
+            mx = fmaxf(redm[r], redm[128 + r]);
+            named_bar_sync(1, 256);            // redm lives in the tail of the P tile: nobody may start writing P earlier
+            const float moff = mx * a.scale_log2e;
+            const f32x2 mo2 = pk2(-moff, -moff);
+#pragma unroll 1
+            for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        float e0, e1;
+                        upk2(fma2(pk2u(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), sc2, mo2), e0, e1);   // one FFMA2 per two scores
+                        w[t] = pack_bf16x2(ex2_approx(e0), ex2_approx(e1));
+                    }
+                    *reinterpret_cast<uint4 *>(Ps + ((c0 / 8 + j) * 128 + r) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(bP);
+            if (threadIdx.x == 0 && qt == 0) MG_ASTAMP(112);
 
-        mbar_wait(&bars[4], 0);
-        tc_fence_after();
-        if (threadIdx.x == 0) MG_ASTAMP(113);
-        uint32_t sv[8];
-        tmem_ld8(trow + HS, sv);               // row sum (all 16 extra columns hold it)
-        constexpr int DH = HS / 2;             // output columns per thread
-        uint32_t v[DH];
+            mbar_wait(bO, qt);
+            tc_fence_after();
+            if (threadIdx.x == 0 && qt == 0) MG_ASTAMP(113);
+            uint32_t sv[8];
+            tmem_ld8(trow + HS, sv);               // row sum (all 16 extra columns hold it)
+            constexpr int DH = HS / 2;             // output columns per thread
+            uint32_t v[DH];
 #pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 16) {
-            uint32_t t[16];
-            tmem_ld16(trow + kh * DH + c0, t);
+            for (int c0 = 0; c0 < DH; c0 += 16) {
+                uint32_t t[16];
+                tmem_ld16(trow + kh * DH + c0, t);
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[c0 + j] = t[j];
-        }
-        tmem_wait_ld();
-        const float inv = 1.0f / __uint_as_float(sv[0]);
-        const int mt = seq * 2 + qt;
+                for (int j = 0; j < 16; j++) v[c0 + j] = t[j];
+            }
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bE);                       // O is in registers: the issuer may overwrite S/O for the next tile
+            const float inv = 1.0f / __uint_as_float(sv[0]);
+            const int mt = seq * 2 + qt;
 #pragma unroll
-        for (int j = 0; j < DH / 8; j++) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-            const int col = head * HS + kh * DH + 8 * j;
-            uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
-            *O = o;
+            for (int j = 0; j < DH / 8; j++) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+                o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+                o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+                o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+                const int col = head * HS + kh * DH + 8 * j;
+                uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
+                *O = o;
+            }
+            if (threadIdx.x == 0 && qt == 0) MG_ASTAMP(114);
         }
     }
-    if (threadIdx.x == 0) MG_ASTAMP(114);
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc<256>(tmem);
 }
 
 template <int HS>
-constexpr int attn_smem_bytes() { return 128 * HS * 2 + 256 * HS * 2 + 256 * (HS + 16) * 2 + 128 * 256 * 2 + 5 * 8 + 16; }
+constexpr int attn_smem_bytes() { return 128 * HS * 2 + 256 * HS * 2 + 256 * (HS + 16) * 2 + 128 * 256 * 2 + 7 * 8 + 16; }
 
 // ---------------------------------------------------------------------------------------------
 // Elementwise / row kernels (HBM-bound).  thread == row.

@@ -14,7 +14,8 @@ from . import _lib
 from .weights import GPTConfig
 
 KERNEL_CLASSES = ["bfs", "observe", "embed", "layernorm", "gemm_qkv", "attention", "gemm_attn_proj",
-                  "gemm_fc_gelu", "gemm_mlp_proj", "head", "sample_step", "post_attn_fused"]
+                  "gemm_fc_gelu", "gemm_mlp_proj", "head", "sample_step", "post_attn_fused", "attention_last_token",
+                  "post_attn_last_token"]
 
 MODE_GREEDY, MODE_PHILOX, MODE_SUPPLIED_Q = 0, 1, 2
 
