@@ -51,6 +51,7 @@ struct Model {
     mg_model_config cfg{};
     int BN = 0, BK = 0, hs = 0;
     bool fused = false;   // C in {160, 256}: post_attn_kernel replaces proj / ln_2 / fc / proj2 / next ln_1
+    bool fuse_qkv = false;  // ... and the next block's c_attn
     float *wte = nullptr, *wpe = nullptr, *lnf = nullptr;
     float *wpe_ti = nullptr;   // wpe re-tiled [2][C/4][128][4] for embed_ln_kernel
     std::vector<Layer> layers;
@@ -160,11 +161,12 @@ static int upload_f32(const float *src, size_t n, float **out)
 
 // Stage stream of post_attn_kernel<C> (fused_kernels.cuh): proj k-steps, then FC(0), FC(1), P2(0), FC(2), ...
 // Wproj[C][C], Wfc[4C][C], Wproj2[C][4C] are torch Linear weights (row = output feature).
-static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, int C, __nv_bfloat16 **out)
+static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, const float *Wqkv_next, int C,
+                                   __nv_bfloat16 **out)
 {
     const int HC = C / 2, NCH = 8, NPROJ = C / 16, NFC = C / 32, NP2 = HC / 16;
     const size_t stage_elems = (size_t)16 * C;   // 32*C bytes
-    const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2)) * stage_elems;
+    const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2) + (Wqkv_next ? 3 * NPROJ : 0)) * stage_elems;
     std::vector<uint16_t> h(total, 0);
     size_t st = 0;
     auto put_kn = [&](size_t base, int kc, int rows, int n, int k8, float v) {   // [kc][rows][8]
@@ -190,6 +192,12 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
         if (j + 1 < NCH) put_fc(j + 1);
         put_p2(j);
     }
+    if (Wqkv_next)   // next block's c_attn [3C][C]: per n-tile of C rows, one k-step per unit (same unit format as proj)
+        for (int t3 = 0; t3 < 3; t3++)
+            for (int ks = 0; ks < NPROJ; ks++, st++)
+                for (int n = 0; n < C; n++)
+                    for (int k = 0; k < 16; k++)
+                        put_kn(st * stage_elems, k / 8, C, n, k % 8, Wqkv_next[(size_t)(t3 * C + n) * C + ks * 16 + k]);
     CU(dalloc(out, total));
     CU(cudaMemcpy(*out, h.data(), total * 2, cudaMemcpyHostToDevice));
     return MG_OK;
@@ -327,9 +335,11 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             prof_end(e);
             for (int l = 0; l < m.cfg.n_layer; l++) {
                 const Layer &L = m.layers[l];
-                GemmArgs g{};
-                g.A = w.XN; g.W = L.wqkv; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
-                if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
+                if (l == 0 || !m.fuse_qkv) {   // blocks >= 1 get q/k/v from the previous block's fused kernel
+                    GemmArgs g{};
+                    g.A = w.XN; g.W = L.wqkv; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
+                    if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
+                }
                 const bool last = l + 1 == m.cfg.n_layer;
                 if (last && e->prune_last) {
                     // last block: Q / attention / c_proj / MLP only for token 255 of each sequence (App. D.2)
@@ -355,7 +365,9 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 PostAttnArgs pa{};
                 pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;
                 pa.next_gain = last ? nullptr : m.layers[l + 1].ln1;
-                pa.xn_out = last ? nullptr : w.XN;
+                pa.xn_out = (last || m.fuse_qkv) ? nullptr : w.XN;
+                pa.qkv_out = (!last && m.fuse_qkv) ? w.QKV : nullptr;
+                pa.n_head = H; pa.hs = hs;
                 pa.timeline = e->d_timeline;
                 if ((rc = launch_post_attn(e, C, pa, MT, false))) return rc;
             }
@@ -656,7 +668,13 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         const float *wproj2 = w;
         if ((rc = upload_packed(w, C, 4 * C, BN, &L.wproj2))) return rc;
         w += 4 * CC;
-        if (m.fused && (rc = upload_post_attn_stream(wproj, wfc, wproj2, C, &L.wstream))) return rc;
+        if (m.fused) {
+            // the fused kernel of block l also computes block l+1's c_attn; its weights sit one block further in the buffer
+            const bool has_next = (&L != &m.layers.back());
+            const float *wqkv_next = has_next ? w + C : nullptr;     // skip ln_1[C] of the next block
+            m.fuse_qkv = getenv("MAPF_GPT_B200_NO_QKV_FUSION") == nullptr;
+            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, C, &L.wstream))) return rc;
+        }
     }
     if ((rc = upload_f32(w, C, &m.lnf))) return rc;
     m.loaded = true;

@@ -30,6 +30,10 @@ struct PostAttnArgs {
     const float *next_gain;        // [C] ln_1 gain of the next block, or nullptr
     __nv_bfloat16 *xn_out;         // A_ti for the next block's QKV GEMM, or nullptr
     long long *timeline;           // test hook: clock64() stamps of CTA 0..3 ([cta][128]); nullptr in production
+    // fused QKV projection of the NEXT block (c_attn, model.py:50): xn never goes to HBM.  The 3 x 2 extra weight stages
+    // follow the 18 regular ones in `wstream`.  nullptr = write xn_out instead.
+    __nv_bfloat16 *qkv_out;        // [seq][3][head][hs/8][256][8]
+    int n_head, hs;
 };
 #define MG_STAMP(id)                                                                     \
     do {                                                                                 \
@@ -105,8 +109,9 @@ struct PostAttnCfg {
     static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
     static constexpr int THREADS = 64 + 256 * NT;
-    static constexpr int NBAR = 2 * STAGES + 2 + NT * 7;
-    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * STAGE_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16;
+    static constexpr int QKV_STAGES = 3 * NPROJ / U;   // next block's c_attn: 3 n-tiles of C columns
+    static constexpr int NBAR = 2 * STAGES + 2 + NT * 10;
+    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * STAGE_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
     static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
     static_assert(TMEM_COLS <= 512, "post_attn_kernel: TMEM budget");
@@ -135,7 +140,12 @@ post_attn_kernel(const PostAttnArgs a)
     uint64_t *bar_a1e = bar_a1f + NT;    // [NT] FC chunk drained to registers (256 arrivals)
     uint64_t *bar_hf = bar_a1e + NT;     // [NT] hidden chunk written to smem (256 arrivals)
     uint64_t *bar_he = bar_hf + NT;      // [NT] hidden chunk consumed by the proj2 UMMAs
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_he + NT);
+    uint64_t *bar_qa = bar_he + NT;      // [NT] fused QKV: LN1_next(x') in smem, accumulator free (256 arrivals)
+    uint64_t *bar_qf = bar_qa + NT;      // [NT] fused QKV: n-tile accumulated
+    uint64_t *bar_qe = bar_qf + NT;      // [NT] fused QKV: n-tile drained (256 arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_qe + NT);
+    uint32_t *qkv_off = tmem_slot + 2;   // uint4 offset of each 8-column group inside a sequence's q/k/v block
+    const bool fuse_qkv = a.qkv_out != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt0 = blockIdx.x * NT;
@@ -155,8 +165,17 @@ post_attn_kernel(const PostAttnArgs a)
             mbar_init(&bar_a1e[t], 256);
             mbar_init(&bar_hf[t], 256);
             mbar_init(&bar_he[t], 1);
+            mbar_init(&bar_qa[t], 256);
+            mbar_init(&bar_qf[t], 1);
+            mbar_init(&bar_qe[t], 256);
         }
         fence_barrier_init();
+    }
+    if (fuse_qkv && threadIdx.x < 3 * C / 8) {
+        const int n = 8 * threadIdx.x;
+        const int which = n / C, rem = n - which * C;
+        const int head = rem / a.hs, d0 = rem - head * a.hs;
+        qkv_off[threadIdx.x] = (uint32_t)(((which * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256);
     }
     if (warp == MMA_WARP) tmem_alloc<K::TMEM_COLS>(tmem_slot);
     tc_fence_before();
@@ -172,7 +191,8 @@ post_attn_kernel(const PostAttnArgs a)
                 bulk_g2s(As + t * K::A_BYTES, a.att + (size_t)(mt0 + t) * C * 128, K::A_BYTES, &bar_att[t]);
             }
             const uint8_t *src = reinterpret_cast<const uint8_t *>(a.wstream);
-            for (int i = 0; i < K::TOTAL_STAGES; i++) {
+            const int n_stages = K::TOTAL_STAGES + (fuse_qkv ? K::QKV_STAGES : 0);
+            for (int i = 0; i < n_stages; i++) {
                 const int s = i % S;
                 mbar_wait(&empty[s], ((i / S) & 1) ^ 1);
                 mbar_expect_tx(&full[s], K::STAGE_BYTES);
@@ -262,6 +282,30 @@ post_attn_kernel(const PostAttnArgs a)
             }
             umma_commit(bar_done);
             MG_STAMP(40);
+            if (fuse_qkv) {
+                // next block's c_attn: [q|k|v] = LN1_next(x') @ Wqkv^T, one C-wide n-tile at a time in the main accumulator
+                for (int t = 0; t < NT; t++) mbar_wait(&bar_qa[t], 0);
+                tc_fence_after();
+                for (int t3 = 0; t3 < 3; t3++) {
+                    for (int st = 0; st < K::NPROJ / U; st++, i++) {
+                        const uint32_t b = stage_wait(i);
+#pragma unroll
+                        for (int t = 0; t < NT; t++) {
+                            if (st == 0 && t3 > 0) {
+                                mbar_wait(&bar_qe[t], (t3 - 1) & 1);
+                                tc_fence_after();
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; u++)
+                                umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
+                                        umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, (st | u) != 0);
+                            if (st == K::NPROJ / U - 1) umma_commit(&bar_qf[t]);
+                        }
+                        umma_commit(&empty[i % S]);
+                    }
+                }
+                MG_STAMP(41);
+            }
         }
     } else {
         // ------------------------------------------------------------------ workers (256 threads per tile)
@@ -399,7 +443,7 @@ post_attn_kernel(const PostAttnArgs a)
                     sq2 = fma2(e1, e1, sq2);
                 }
             }
-            if (a.xn_out != nullptr) {
+            if (a.xn_out != nullptr || fuse_qkv) {
                 {
                     float s0, s1, q0, q1;
                     upk2(sum2, s0, s1);
@@ -420,10 +464,41 @@ post_attn_kernel(const PostAttnArgs a)
                     tmem_ld16(trow + c0, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 2; j++)
-                        O[(size_t)(c0 / 8 + j) * 128] =
-                            ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
+                    for (int j = 0; j < 2; j++) {
+                        const uint4 o = ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
+                        if (fuse_qkv) *reinterpret_cast<uint4 *>(At + ((c0 / 8 + j) * 128 + r) * 16) = o;
+                        else O[(size_t)(c0 / 8 + j) * 128] = o;
+                    }
                 }
+            }
+        }
+        if (fuse_qkv) {
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&bar_qa[t]);
+            const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
+            uint4 *Oseq = reinterpret_cast<uint4 *>(a.qkv_out) + (size_t)seq * (3 * C / 8) * 256 + tok;
+#pragma unroll 1
+            for (int t3 = 0; t3 < 3; t3++) {
+                mbar_wait(&bar_qf[t], t3 & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + c0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                        Oseq[qkv_off[(t3 * C + c0) / 8 + j]] = o;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bar_qe[t]);
             }
         }
     }
