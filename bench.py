@@ -260,6 +260,9 @@ def main():
         kflops = {"gemm_qkv": 2 * 3 * C * C, "gemm_attn_proj": 2 * C * C, "gemm_fc_gelu": 2 * 4 * C * C,
                   "gemm_mlp_proj": 2 * 4 * C * C, "attention": 4 * T * C,
                   "post_attn_fused": 2 * 9 * C * C}   # per token
+        fuse_qkv = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
+        if fuse_qkv:
+            kflops["post_attn_fused"] += 2 * 3 * C * C       # + the next block's c_attn
         kern = {}
         for k, v in ktimes.items():
             if v["launches"]:
@@ -271,13 +274,17 @@ def main():
                 kern[k] = ent
         dom = max((k for k in kern if k in kflops), key=lambda k: kern[k]["ms_total"])
         achieved = kern[dom]["tflops"]
+        traffic = None
+        tfile = ROOT / "profiles" / "dram_traffic.json"       # dram__bytes_read+write per launch from the committed ncu capture
+        if tfile.exists():
+            traffic = json.load(open(tfile)).get(f"{args.model}:{dom}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, E_gpu),
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": round(achieved / pk["tflops"], 4), "traffic": None, "peak_source": pk["source"],
+                         "frac": round(achieved / pk["tflops"], 4), "traffic": traffic, "peak_source": pk["source"],
                          "whole_step_tflops": round(value / world * Fx / 1e12, 1),
                          "whole_step_frac": round(value / world * Fx / 1e12 / pk["tflops"], 4),
                          "flops_per_agent_step_executed": Fx, "flops_per_agent_step_reference": F,

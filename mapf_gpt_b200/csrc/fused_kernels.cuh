@@ -40,28 +40,6 @@ struct PostAttnArgs {
         if (a.timeline != nullptr && blockIdx.x < 4) a.timeline[blockIdx.x * 128 + (id)] = clock64(); \
     } while (0)
 
-// erf-GELU on a PAIR of values with packed fp32x2 math (FFMA2): erf(z) ~ z * P(z^2), odd degree-17 polynomial on
-// |z| <= 3 (z clamped by one saturating FFMA per element), FMA-only, no MUFU.  Max |gelu error| 5e-5 over all x;
-// the result is rounded to bf16 (rel. 4e-3) right after, see DESIGN.md "Tolerance".
-__device__ __forceinline__ f32x2 gelu2(float x0, float x1)
-{
-    const float w0 = __saturatef(fmaf(x0, 0.70710678118654752440f / 6.0f, 0.5f));
-    const float w1 = __saturatef(fmaf(x1, 0.70710678118654752440f / 6.0f, 0.5f));
-    const f32x2 z = fma2(pk2(w0, w1), pk2(6.0f, 6.0f), pk2(-3.0f, -3.0f));
-    const f32x2 u = mul2(z, z);
-    f32x2 p = pk2(3.9138299712249136e-08f, 3.9138299712249136e-08f);
-    p = fma2(p, u, pk2(-1.8835556829799316e-06f, -1.8835556829799316e-06f));
-    p = fma2(p, u, pk2(4.0097045712172985e-05f, 4.0097045712172985e-05f));
-    p = fma2(p, u, pk2(-0.0005030000465922058f, -0.0005030000465922058f));
-    p = fma2(p, u, pk2(0.004197265952825546f, 0.004197265952825546f));
-    p = fma2(p, u, pk2(-0.02500014565885067f, -0.02500014565885067f));
-    p = fma2(p, u, pk2(0.11093290150165558f, 0.11093290150165558f));
-    p = fma2(p, u, pk2(-0.3752213716506958f, -0.3752213716506958f));
-    p = fma2(p, u, pk2(1.128251075744629f, 1.128251075744629f));
-    const f32x2 hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
-    return fma2(hx, mul2(z, p), hx);
-}
-
 // (v - mean) * rstd * gain for 8 consecutive columns -> 8 bf16 (one 16-byte store); a = rstd, b = -mean * rstd
 __device__ __forceinline__ uint4 ln_pack8(const uint32_t *v, f32x2 a, f32x2 b, const float4 g0, const float4 g1)
 {

@@ -25,7 +25,28 @@ struct GemmArgs {
     int dbg_swap_lbo_sbo;    // test hook: swap descriptor fields (layout bring-up)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU on a PAIR of values with packed fp32x2 math (FFMA2): erf(z) ~ z * P(z^2), odd degree-17 polynomial on
+// |z| <= 3 (z clamped by one saturating FFMA per element), FMA-only, no MUFU.  Max |gelu error| 5e-5 over all x;
+// the result is rounded to bf16 (rel. 4e-3) right after, see DESIGN.md "Tolerance".
+__device__ __forceinline__ f32x2 gelu2(float x0, float x1)
+{
+    const float w0 = __saturatef(fmaf(x0, 0.70710678118654752440f / 6.0f, 0.5f));
+    const float w1 = __saturatef(fmaf(x1, 0.70710678118654752440f / 6.0f, 0.5f));
+    const f32x2 z = fma2(pk2(w0, w1), pk2(6.0f, 6.0f), pk2(-3.0f, -3.0f));
+    const f32x2 u = mul2(z, z);
+    f32x2 p = pk2(3.9138299712249136e-08f, 3.9138299712249136e-08f);
+    p = fma2(p, u, pk2(-1.8835556829799316e-06f, -1.8835556829799316e-06f));
+    p = fma2(p, u, pk2(4.0097045712172985e-05f, 4.0097045712172985e-05f));
+    p = fma2(p, u, pk2(-0.0005030000465922058f, -0.0005030000465922058f));
+    p = fma2(p, u, pk2(0.004197265952825546f, 0.004197265952825546f));
+    p = fma2(p, u, pk2(-0.02500014565885067f, -0.02500014565885067f));
+    p = fma2(p, u, pk2(0.11093290150165558f, 0.11093290150165558f));
+    p = fma2(p, u, pk2(-0.3752213716506958f, -0.3752213716506958f));
+    p = fma2(p, u, pk2(1.128251075744629f, 1.128251075744629f));
+    const f32x2 hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
+    return fma2(hx, mul2(z, p), hx);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // C[128 x BN] tile = A[128 x K] * W[BN x K]^T, bf16 operands, fp32 accumulation in TMEM.
@@ -143,10 +164,10 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     uint4 o;
-                    o.x = pack_bf16x2(gelu_erf(__uint_as_float(v[8 * j + 0])), gelu_erf(__uint_as_float(v[8 * j + 1])));
-                    o.y = pack_bf16x2(gelu_erf(__uint_as_float(v[8 * j + 2])), gelu_erf(__uint_as_float(v[8 * j + 3])));
-                    o.z = pack_bf16x2(gelu_erf(__uint_as_float(v[8 * j + 4])), gelu_erf(__uint_as_float(v[8 * j + 5])));
-                    o.w = pack_bf16x2(gelu_erf(__uint_as_float(v[8 * j + 6])), gelu_erf(__uint_as_float(v[8 * j + 7])));
+                    o.x = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])));
+                    o.y = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])));
+                    o.z = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])));
+                    o.w = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
                     O[(size_t)j * 128] = o;
                 }
             } else {  // EPI_QKV: scatter into [seq][3][head][hs/8][256][8]
@@ -197,6 +218,27 @@ __device__ __forceinline__ float ex2_approx(float x)
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x for a PAIR of non-positive inputs on the FMA/ALU pipes instead of MUFU (the softmax is MUFU-bound: 16 ex2/clk/SM).
+// Cody-Waite: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], degree-3 polynomial for 2^f (max rel.
+// error 8e-5, far below the bf16 rounding of P), exponent patched in with one integer shift-add per element.
+__device__ __forceinline__ void exp2_poly2(f32x2 x, float &r0, float &r1)
+{
+    float x0, x1;
+    upk2(x, x0, x1);
+    const f32x2 xc = pk2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const f32x2 t = add2(xc, pk2(12582912.0f, 12582912.0f));
+    const f32x2 n = add2(t, pk2(-12582912.0f, -12582912.0f));
+    const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), xc);
+    f32x2 p = fma2(pk2(0.05508868396282196f, 0.05508868396282196f), f, pk2(0.24260404706001282f, 0.24260404706001282f));
+    p = fma2(p, f, pk2(0.6932762265205383f, 0.6932762265205383f));
+    p = fma2(p, f, pk2(0.9999289512634277f, 0.9999289512634277f));
+    uint32_t t0, t1, p0, p1;
+    upk2u(t, t0, t1);
+    upk2u(p, p0, p1);
+    r0 = __uint_as_float(p0 + (t0 << 23));
+    r1 = __uint_as_float(p1 + (t1 << 23));
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c)
@@ -335,9 +377,16 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
                     uint32_t w[4];
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
+                        const f32x2 xs = fma2(pk2u(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), sc2, mo2);   // one FFMA2 per two scores
                         float e0, e1;
-                        upk2(fma2(pk2u(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), sc2, mo2), e0, e1);   // one FFMA2 per two scores
-                        w[t] = pack_bf16x2(ex2_approx(e0), ex2_approx(e1));
+                        if (t & 1) {           // every other pair on the FMA/ALU pipes: balances MUFU against issue slots
+                            exp2_poly2(xs, e0, e1);
+                        } else {
+                            upk2(xs, e0, e1);
+                            e0 = ex2_approx(e0);
+                            e1 = ex2_approx(e1);
+                        }
+                        w[t] = pack_bf16x2(e0, e1);
                     }
                     *reinterpret_cast<uint4 *>(Ps + ((c0 / 8 + j) * 128 + r) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
