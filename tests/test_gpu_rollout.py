@@ -220,3 +220,19 @@ def test_baseline_size_properties(built, name, n, envs, model):
             a[:, 125 + 10 * s:130 + 10 * s] = 0; b[:, 125 + 10 * s:130 + 10 * s] = 0
         assert (a == b).all()
     eng.close(); eng2.close()
+
+
+def test_reference_shaped_entry_points(built):
+    """example.py (reference flags) in both modes: device-resident rollout and the run_episode-style act() loop."""
+    import json, subprocess, sys
+    root = Path(__file__).resolve().parents[1]
+    for extra in ([], ["--via-act"]):
+        out = subprocess.run([sys.executable, str(root / "example.py"), "--map_name", "validation-random-seed-000",
+                              "--num_agents", "8", "--max_episode_steps", "6", "--seed", "1"] + extra,
+                             capture_output=True, text=True, timeout=600, cwd=root)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        assert res["num_agents"] == 8 and 1 <= res["ep_length"] <= 6 and 0.0 <= res["ISR"] <= 1.0
+    names = subprocess.run([sys.executable, str(root / "example.py"), "--show_map_names"], capture_output=True, text=True,
+                           timeout=120, cwd=root).stdout.split()
+    assert "validation-mazes-seed-000" in names and "wfi_warehouse" in names
