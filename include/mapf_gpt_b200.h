@@ -112,6 +112,9 @@ int mg_engine_generate_observations(mg_engine *e, int8_t *out_tokens);
  * torch.multinomial's argmax(p/q) for the same q.  actions_out / logits_out: HOST, may be NULL
  * (num_envs*max_agents int32 / *5 fp32). */
 int mg_engine_act(mg_engine *e, int mode, const float *q_exp, int32_t *actions_out, float *logits_out);
+/* act_batch may address a subset of the slots (inference.py:151-172 touches only the slots it is given): slots whose mask
+ * byte is 0 are skipped by update / tokenizer / sampling / step until the mask changes.  mask: HOST, num_envs bytes; NULL = all. */
+int mg_engine_set_active(mg_engine *e, const uint8_t *mask);
 int mg_engine_set_seed(mg_engine *e, uint64_t seed);
 /* global id of slot 0 (env-sharded multi-GPU runs: the Philox stream follows the env, not the rank) */
 int mg_engine_set_env_offset(mg_engine *e, int first_global_env);

@@ -53,6 +53,7 @@ _SIGS = {
     "mg_engine_update_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_engine_generate_observations": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_engine_act": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_engine_set_active": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_engine_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "mg_engine_set_env_offset": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_engine_set_max_episode_steps": (C.c_int, [C.c_void_p, C.c_int]),

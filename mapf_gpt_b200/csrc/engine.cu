@@ -92,6 +92,8 @@ struct mg_engine {
     float last_total_ms = 0.f, last_phase_ms[3] = {0.f, 0.f, 0.f};
     float kc_ms[KC_COUNT] = {0};
     long long *d_timeline = nullptr;   // test hook (mg_test_timeline)
+    CUtensorMap map_c2g{}, map_loc{};  // TMA descriptors of the FOV-window fields (observe_tma_kernel)
+    bool use_tma = false;
     long long kc_n[KC_COUNT] = {0};
 };
 
@@ -417,9 +419,47 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
 static size_t bfs_smem(const EnvState &s) { return (size_t)s.H * s.P * 7 + 16; }
 static size_t step_smem(const EnvState &s) { return (size_t)s.H * s.P * 4 + (size_t)s.N * 5 + 16; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_window_maps(mg_engine *e)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+        return fail(MG_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode_tiled_fn enc = reinterpret_cast<encode_tiled_fn>(fn);
+    const EnvState &s = e->s;
+    const cuuint32_t box[3] = {24, 11, 1}, estr[3] = {1, 1, 1};   // 24 cols: 8-aligned start + 11-wide window (see kernel)
+    {   // cost-to-go fields: [E*N planes][H rows][P cols] u16
+        const cuuint64_t dims[3] = {(cuuint64_t)s.P, (cuuint64_t)s.H, (cuuint64_t)s.E * s.N};
+        const cuuint64_t strides[2] = {(cuuint64_t)s.P * 2, (cuuint64_t)s.H * s.P * 2};
+        if (enc(&e->map_c2g, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, s.c2g, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(MG_ERR_CUDA, "cuTensorMapEncodeTiled(c2g) failed");
+    }
+    {   // agent-id maps: [E planes][H][P] i16
+        const cuuint64_t dims[3] = {(cuuint64_t)s.P, (cuuint64_t)s.H, (cuuint64_t)s.E};
+        const cuuint64_t strides[2] = {(cuuint64_t)s.P * 2, (cuuint64_t)s.H * s.P * 2};
+        if (enc(&e->map_loc, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, s.loc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(MG_ERR_CUDA, "cuTensorMapEncodeTiled(loc) failed");
+    }
+    return MG_OK;
+}
+
 static int launch_observe(mg_engine *e, bool update, bool tokens)
 {
     if (e->n_envs == 0) return fail(MG_ERR_STATE, "no environment has been reset");
+    if (tokens && e->use_tma) {
+        prof_begin(e, KC_OBSERVE);
+        if (update) observe_tma_kernel<true><<<e->n_envs, 256, 0, e->stream>>>(e->s, e->map_c2g, e->map_loc);
+        else observe_tma_kernel<false><<<e->n_envs, 256, 0, e->stream>>>(e->s, e->map_c2g, e->map_loc);
+        prof_end(e);
+        CU(cudaGetLastError());
+        return MG_OK;
+    }
     prof_begin(e, KC_OBSERVE);
     if (update && tokens) observe_kernel<true, true><<<e->n_envs, 256, 0, e->stream>>>(e->s);
     else if (update) observe_kernel<true, false><<<e->n_envs, 256, 0, e->stream>>>(e->s);
@@ -554,6 +594,7 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
     ok = ok && dalloc(&s.hist, EN * 8) == cudaSuccess && dalloc(&s.nextb, EN) == cudaSuccess;
     ok = ok && dalloc(&s.act, EN) == cudaSuccess && dalloc(&s.nag, (size_t)s.E) == cudaSuccess;
     ok = ok && dalloc(&s.dirty, EN) == cudaSuccess && dalloc(&s.tokens, EN * 256) == cudaSuccess;
+    ok = ok && dalloc(&s.active, (size_t)s.E) == cudaSuccess;
     ok = ok && dalloc(&s.logits, EN * 8) == cudaSuccess;
     ok = ok && dalloc(&s.steps, (size_t)s.E) == cudaSuccess && dalloc(&s.done, (size_t)s.E) == cudaSuccess;
     ok = ok && dalloc(&s.arrive, EN) == cudaSuccess && dalloc(&s.agent_steps, (size_t)s.E) == cudaSuccess;
@@ -563,6 +604,7 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
     ok = ok && dalloc(&e->d_q, EN * 5) == cudaSuccess && dalloc(&e->d_metrics, (size_t)s.E * 8) == cudaSuccess;
     if (ok) {
         cudaMemset(s.nag, 0, s.E * 4);
+        cudaMemset(s.active, 1, s.E);
         cudaMemset(s.vocab_err, 0, 4);
         cudaMemset(s.tokens, 66, EN * 256);
         cudaMemset(s.logits, 0, EN * 8 * 4);
@@ -581,6 +623,16 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
         mg_engine_destroy(e);
         return nullptr;
     }
+    {   // FOV windows by TMA tiled loads (default); MAPF_GPT_B200_NO_TMA_WINDOWS=1 selects the plain-load tokenizer
+        const char *no_tma = getenv("MAPF_GPT_B200_NO_TMA_WINDOWS");
+        if (!(no_tma && no_tma[0] == '1')) {
+            if (make_window_maps(e) != MG_OK) {
+                mg_engine_destroy(e);
+                return nullptr;
+            }
+            e->use_tma = true;
+        }
+    }
     return e;
 }
 
@@ -592,7 +644,7 @@ void mg_engine_destroy(mg_engine *e)
     EnvState &s = e->s;
     cudaFree(s.obst); cudaFree(s.loc); cudaFree(s.c2g); cudaFree(s.pos); cudaFree(s.goal); cudaFree(s.hist);
     cudaFree(s.nextb); cudaFree(s.act); cudaFree(s.nag); cudaFree(s.dirty); cudaFree(s.tokens); cudaFree(s.logits);
-    cudaFree(s.steps); cudaFree(s.done); cudaFree(s.arrive); cudaFree(s.agent_steps); cudaFree(s.vocab_err);
+    cudaFree(s.active); cudaFree(s.steps); cudaFree(s.done); cudaFree(s.arrive); cudaFree(s.agent_steps); cudaFree(s.vocab_err);
     cudaFree(e->d_pos_in); cudaFree(e->d_goal_in); cudaFree(e->d_act_in); cudaFree(e->d_step_act); cudaFree(e->d_q);
     cudaFree(e->d_metrics);
     Model &m = e->model;
@@ -769,6 +821,16 @@ int mg_engine_generate_observations(mg_engine *e, int8_t *out_tokens)
     if (out_tokens)
         CU(cudaMemcpyAsync(out_tokens, e->s.tokens, (size_t)e->n_envs * e->s.N * 256, cudaMemcpyDeviceToHost, e->stream));
     return check_vocab(e);
+}
+
+int mg_engine_set_active(mg_engine *e, const uint8_t *mask)
+{
+    if (!e) return fail(MG_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (mask) CU(cudaMemcpyAsync(e->s.active, mask, (size_t)e->n_envs, cudaMemcpyHostToDevice, e->stream));
+    else CU(cudaMemsetAsync(e->s.active, 1, (size_t)e->s.E, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MG_OK;
 }
 
 int mg_engine_set_seed(mg_engine *e, uint64_t seed)

@@ -9,8 +9,11 @@
 //   pos, goal  short2 [E][N] (x = row, y = col)                       hist u8 [E][N][8] (5 used)
 //   nextb u8 [E][N]          act i32 [E][N]                           tokens u8 [E*N][256]
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "ptx.cuh"
 
 namespace mg {
 
@@ -24,6 +27,7 @@ struct EnvState {
     uint8_t *nextb;
     int32_t *act;
     int32_t *nag;        // agents per env (0 = slot unused)
+    uint8_t *active;     // [E] slots taking part in the current call (act_batch may address a subset of the slots)
     uint8_t *dirty;      // [E][N] cost-to-go must be recomputed
     uint8_t *tokens;
     float *logits;       // [E*N][8]
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) set_state_kernel(EnvState s, const int32_
 {
     const int e = blockIdx.x;
     const int n = s.nag[e];
-    if (n == 0) return;
+    if (n == 0 || !s.active[e]) return;
     const int cells = s.H * s.P;
     int16_t *loc = s.loc + (size_t)e * cells;
     if (pos_in) {
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(256) observe_kernel(EnvState s)
 {
     const int e = blockIdx.x;
     const int n = s.nag[e];
-    if (n == 0) return;
+    if (n == 0 || !s.active[e]) return;
     const int cells = s.H * s.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ __align__(16) uint8_t tokbuf[8][256];
@@ -253,6 +257,139 @@ __global__ void __launch_bounds__(256) observe_kernel(EnvState s)
 }
 
 // ------------------------------------------------------------------------------------------------
+// observe_tma_kernel: same results as observe_kernel<kUpdate, true>, but each agent's two 11x11 FOV windows (its own
+// cost-to-go field and the env's agent-id map) are pulled into shared memory by TMA tiled loads: one 3-D box
+// {24 cols, 11 rows, 1 plane} of u16/i16 per field.  The box must START on a 16-byte boundary in the innermost dimension
+// (measured: an unaligned start coordinate traps with "illegal instruction"), so the box starts at the 8-column boundary
+// below the window and is 24 columns wide (22-byte window + up to 14 bytes of lead-in, rounded to a multiple of 16 B);
+// columns past the grid pitch are zero-filled by the TMA unit and never read.  One block per env, one warp per agent at a
+// time, double-buffered: the boxes of the warp's NEXT agent are in flight while it tokenizes the current one.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <bool kUpdate>
+__global__ void __launch_bounds__(256) observe_tma_kernel(EnvState s, const __grid_constant__ CUtensorMap map_c2g,
+                                                          const __grid_constant__ CUtensorMap map_loc)
+{
+    const int e = blockIdx.x;
+    const int n = s.nag[e];
+    if (n == 0 || !s.active[e]) return;
+    const int cells = s.H * s.P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ __align__(128) uint16_t win[8][2][2][320];   // [warp][buffer][field: 0 c2g, 1 loc][11 rows x 24 cols], 640-byte blocks (128-byte aligned TMA destinations)
+    __shared__ __align__(16) uint8_t tokbuf[8][256];
+    __shared__ int sel[8][16];
+    __shared__ uint64_t bars[8][2];
+
+    if (lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        fence_barrier_init();
+    }
+    if (kUpdate) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int idx = e * s.N + i;
+            const int a = s.act[idx];
+            uint8_t *h = s.hist + (size_t)idx * 8;
+            h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = h[4];
+            h[4] = (a >= 0 && a <= 4) ? (uint8_t)(45 + a) : (uint8_t)44;
+            const uint16_t *F = s.c2g + (size_t)idx * cells;
+            const short2 p = s.pos[idx];
+            const int cur = field_dist(F, p.x, p.y, s.H, s.W, s.P);
+            int bits = 0;
+#pragma unroll
+            for (int m = 1; m < 5; m++) {
+                const int nb = field_dist(F, p.x + c_moves[m][0], p.y + c_moves[m][1], s.H, s.W, s.P);
+                bits = (bits << 1) | ((nb >= 0 && cur > nb) ? 1 : 0);
+            }
+            s.nextb[idx] = (uint8_t)bits;
+        }
+    }
+    __syncthreads();
+
+    auto issue = [&](int i, int buf) {
+        if (lane == 0) {
+            const short2 p = s.pos[e * s.N + i];
+            mbar_expect_tx(&bars[warp][buf], 2 * 11 * 24 * 2);
+            tma_load_3d(&win[warp][buf][0][0], &map_c2g, (p.y - 5) & ~7, p.x - 5, e * s.N + i, &bars[warp][buf]);
+            tma_load_3d(&win[warp][buf][1][0], &map_loc, (p.y - 5) & ~7, p.x - 5, e, &bars[warp][buf]);
+        }
+    };
+    const int nw = blockDim.x >> 5;
+    if (warp < n) issue(warp, 0);
+    int it = 0;
+    for (int i = warp; i < n; i += nw, it++) {
+        const int buf = it & 1;
+        if (i + nw < n) issue(i + nw, buf ^ 1);
+        mbar_wait(&bars[warp][buf], (it >> 1) & 1);
+        const int idx = e * s.N + i;
+        const short2 p = s.pos[idx];
+        const int lead = (p.y - 5) & 7;      // window column 0 inside the 8-aligned box
+        const uint16_t *wc = &win[warp][buf][0][0] + lead;
+        const int16_t *wl = reinterpret_cast<const int16_t *>(&win[warp][buf][1][0]) + lead;
+        const int mid = wc[5 * 24 + 5];
+        uint8_t *tb = tokbuf[warp];
+        unsigned key[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int w = lane + 32 * t;
+            key[t] = 0xFFFFFFFFu;
+            if (w < 121) {
+                const int wi = w / 11, wj = w - wi * 11;
+                const int v = wc[wi * 24 + wj];
+                int tok;
+                if (v == 0xFFFF) tok = 41;
+                else {
+                    const int d = v - mid;
+                    tok = d > 20 ? 43 : (d < -20 ? 42 : d + 20);
+                }
+                tb[w] = (uint8_t)tok;
+                const int id = wl[wi * 24 + wj];
+                if (id >= 0) key[t] = ((unsigned)(abs(wi - 5) + abs(wj - 5)) << 16) | (unsigned)id;
+            }
+        }
+        int count = 0;
+#pragma unroll 1
+        for (int k = 0; k < 13; k++) {
+            const unsigned lm = min(min(key[0], key[1]), min(key[2], key[3]));
+            const unsigned m = __reduce_min_sync(0xffffffffu, lm);
+            if (m == 0xFFFFFFFFu) break;
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (key[t] == m) key[t] = 0xFFFFFFFFu;
+            if (lane == 0) sel[warp][k] = (int)(m & 0xFFFF);
+            count++;
+        }
+        __syncwarp();
+        for (int t = lane; t < 135; t += 32) {
+            uint8_t tok = 66;
+            const int slot = t / 10, f = t - slot * 10;
+            if (slot < count) {
+                const int j = e * s.N + sel[warp][slot];
+                if (f < 4) {
+                    const short2 q = (f < 2) ? s.pos[j] : s.goal[j];
+                    int d = ((f & 1) ? q.y - p.y : q.x - p.x);
+                    if (f >= 2) d = max(-20, min(20, d));
+                    else if (d < -20 || d > 20) atomicExch(s.vocab_err, 1);
+                    tok = (uint8_t)(d + 20);
+                } else if (f < 9) tok = s.hist[(size_t)j * 8 + (f - 4)];
+                else tok = (uint8_t)(50 + s.nextb[j]);
+            }
+            tb[121 + t] = tok;
+        }
+        __syncwarp();
+        reinterpret_cast<uint2 *>(s.tokens + (size_t)idx * 256)[lane] = reinterpret_cast<const uint2 *>(tb)[lane];
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (counter-based; one independent stream per (seed, env, agent, step))
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -299,7 +436,7 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
     extern __shared__ __align__(16) uint8_t sm[];
     const int e = blockIdx.x;
     const int n = s.nag[e];
-    if (n == 0) return;
+    if (n == 0 || !s.active[e]) return;
     const int cells = s.H * s.P;
     int *claim = reinterpret_cast<int *>(sm);                 // [cells]
     int *tgt = claim + cells;                                 // [N]

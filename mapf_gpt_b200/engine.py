@@ -145,6 +145,11 @@ class RolloutEngine:
     def synchronize(self):
         _lib.check(self._L.mg_engine_synchronize(self._h))
 
+    def set_active(self, mask=None):
+        """Restrict the next calls to the slots whose mask entry is non-zero (None = all slots)."""
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        _lib.check(self._L.mg_engine_set_active(self._h, _ptr(m)))
+
     def set_seed(self, seed: int):
         _lib.check(self._L.mg_engine_set_seed(self._h, seed))
 

@@ -109,6 +109,7 @@ class MAPFGPTInference:
         self._slot_n: dict = {}         # slot key -> agent count
         self._last_actions: dict = {}
         self._step = 0
+        self._all_active = True
 
     # ------------------------------------------------------------------ reference surface
     @staticmethod
@@ -124,6 +125,7 @@ class MAPFGPTInference:
         self._slots, self._slot_n, self._last_actions = {}, {}, {}
         self.torch_generator.manual_seed(0)
         self._step = 0
+        self._all_active = True
 
     def act(self, observations):
         return self.act_batch([observations])[0]
@@ -152,6 +154,11 @@ class MAPFGPTInference:
             counts.append(n)
         self._pos[:E], self._goals[:E] = pos, goal
         mode, q = self._draw(positions, counts, E, N)
+        present = np.zeros(E, dtype=np.uint8)
+        present[[self._slots[k] for k in positions]] = 1
+        if not present.all() or not self._all_active:          # only the addressed slots are updated (inference.py:158-160)
+            eng.set_active(None if present.all() else present)
+            self._all_active = bool(present.all())
         acts = eng.act_host(pos, goal, mode, q)
         results = []
         for key, n in zip(positions, counts):

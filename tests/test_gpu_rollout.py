@@ -236,3 +236,38 @@ def test_reference_shaped_entry_points(built):
     names = subprocess.run([sys.executable, str(root / "example.py"), "--show_map_names"], capture_output=True, text=True,
                            timeout=120, cwd=root).stdout.split()
     assert "validation-mazes-seed-000" in names and "wfi_warehouse" in names
+
+
+def test_act_batch_multi_slot_keys_and_partial_calls(built):
+    """act_batch(observations_list, positions): persistent slot keys, ragged agent counts, a slot missing from a call keeps
+    its history (inference.py:151-172)."""
+    import oracle
+    from mapf_gpt_b200 import maps
+    from mapf_gpt_b200.inference import MAPFGPTInference, MAPFGPTInferenceConfig
+    cfg, sd = sharp_model()
+    m = maps.load_map("validation-random-seed-003")
+    grid = m["grid"]
+    ns = {"a": 9, "b": 5, 7: 12}
+    inst = {k: maps.sample_instance(m, n, 3, i) for i, (k, n) in enumerate(ns.items())}
+    algo = MAPFGPTInference(MAPFGPTInferenceConfig(device="cuda"), net=(sd, cfg), do_sample=False)
+    algo.reset_states()
+    orc, pos, last = {}, {}, {}
+    for k, (st, gl) in inst.items():
+        orc[k] = oracle.ObsOracle(grid); orc[k].create_agents(st, gl)
+        pos[k], last[k] = st.copy(), np.full(len(st), -1, np.int32)
+
+    def obs_of(k):
+        return [{"global_obstacles": grid, "global_xy": tuple(int(v) for v in pos[k][i]),
+                 "global_target_xy": tuple(int(v) for v in inst[k][1][i])} for i in range(len(pos[k]))]
+
+    for step, keys in enumerate([["a", "b", 7], ["a", 7], ["b", "a", 7], ["b"]]):
+        res = algo.act_batch([obs_of(k) for k in keys], positions=keys)
+        toks = algo._engine.tokens()
+        for k, acts in zip(keys, res):
+            assert len(acts) == ns[k] and all(0 <= a <= 4 for a in acts)
+            orc[k].update_agents(pos[k], inst[k][1], last[k])
+            e = algo._slots[k]
+            assert (toks[e, :ns[k]] == orc[k].generate_observations()).all(), (step, k)
+            last[k] = np.asarray(acts, np.int32)
+            pos[k], _ = oracle.pogema_step_soft(grid, pos[k], last[k])
+    assert algo.act_batch([]) == []
