@@ -75,8 +75,10 @@ void mg_default_params(mg_params *p);
 int mg_device_count(void);
 
 /* ---- engine lifetime ------------------------------------------------------------ */
-/* Capacity is fixed at creation: E env slots x N agents on H x W padded grids
- * (H, W <= 74: the cost-to-go field is then one BFS per agent per goal). */
+/* Capacity is fixed at creation: E env slots x N agents on H x W padded grids, 11..512 cells per side.
+ * H, W <= 74: the cost-to-go field is one BFS per agent per goal over the whole grid.  Larger grids run the
+ * windowed machinery of observation_generator.cpp:43-286 (per-map precompute tables, per-agent partial fields that are
+ * recomputed when the goal changes or the FOV leaves the window). */
 mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int W, const mg_params *params);
 void mg_engine_destroy(mg_engine *e);
 
@@ -141,7 +143,10 @@ int mg_engine_act_host(mg_engine *e, const int32_t *pos_xy, const int32_t *goal_
 /* ---- state read-back ------------------------------------------------------------------ */
 int mg_engine_get_positions(mg_engine *e, int32_t *pos_xy_out);
 int mg_engine_get_tokens(mg_engine *e, int8_t *out_tokens);
-int mg_engine_get_cost2go(mg_engine *e, int env, int agent, uint16_t *out_hw);
+int mg_engine_get_cost2go(mg_engine *e, int env, int agent, uint16_t *out_hw);   /* grids <= 74 cells per side */
+/* Cost2GoPartial (observation_generator.h:67-82): window bounds {left,right,top,bottom} (inclusive) and the rows x cols
+ * field of one agent; returns rows*cols (negative on error).  Works for every grid size. */
+int mg_engine_get_partial(mg_engine *e, int env, int agent, int32_t *bounds4, uint16_t *out, int cap);
 /* per-slot episode metrics, doubles [num_envs][8]:
  * 0 ep_length, 1 CSR, 2 ISR, 3 SoC, 4 makespan, 5 agents on goal now, 6 agent-steps executed, 7 n_agents */
 int mg_engine_get_metrics(mg_engine *e, double *out);

@@ -64,6 +64,7 @@ _SIGS = {
     "mg_engine_get_positions": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_engine_get_tokens": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_engine_get_cost2go": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mg_engine_get_partial": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "mg_engine_get_metrics": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_engine_synchronize": (C.c_int, [C.c_void_p]),
     "mg_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -93,7 +93,10 @@ struct mg_engine {
     float kc_ms[KC_COUNT] = {0};
     long long *d_timeline = nullptr;   // test hook (mg_test_timeline)
     CUtensorMap map_c2g{}, map_loc{};  // TMA descriptors of the FOV-window fields (observe_tma_kernel)
+    std::vector<std::vector<uint8_t>> map_grids;   // large maps: host copies of the distinct grids (precompute tables per map)
+    std::vector<uint16_t *> map_pre;               // device K x K tables
     bool use_tma = false;
+    int n_sms = 148;
     long long kc_n[KC_COUNT] = {0};
 };
 
@@ -417,7 +420,68 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
 
 // ------------------------------------------------------------------------------------------- env helpers
 static size_t bfs_smem(const EnvState &s) { return (size_t)s.H * s.P * 7 + 16; }
-static size_t step_smem(const EnvState &s) { return (size_t)s.H * s.P * 4 + (size_t)s.N * 5 + 16; }
+static size_t step_smem(const EnvState &s) { return (size_t)s.N * 5 + 16; }
+static size_t partial_smem(const EnvState &s)
+{
+    const size_t W = 2 * s.gs + 1, Q = W * W + 4 * W + 8;
+    auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    return al(W * W * 2) + al((size_t)(s.gs + 1) * (s.gs + 1) * 2) + 2 * al(Q * 2) + al((4 * W + 4) * 4) + al((4 * W + 4) * 2) + 16;
+}
+static const int MG_MAX_MAPS = 64;
+
+// (re)compute cost-to-go fields: whole-grid BFS for small grids, windowed partials for large ones
+static int launch_fields(mg_engine *e, int first_env, int n_envs, int only_dirty)
+{
+    EnvState &s = e->s;
+    prof_begin(e, KC_BFS);
+    if (s.large) partial_kernel<<<n_envs * s.N, 256, partial_smem(s), e->stream>>>(s, first_env, only_dirty);
+    else bfs_kernel<<<n_envs * s.N, 128, bfs_smem(s), e->stream>>>(s, first_env, only_dirty);
+    prof_end(e);
+    CU(cudaGetLastError());
+    return MG_OK;
+}
+
+// precompute_cost2go (cpp:43-113) for one distinct large map; returns its slot
+static int add_large_map(mg_engine *e, const uint8_t *grid_pitched, int *slot_out)
+{
+    EnvState &s = e->s;
+    const size_t cells = (size_t)s.H * s.P;
+    for (size_t m = 0; m < e->map_grids.size(); m++)
+        if (memcmp(e->map_grids[m].data(), grid_pitched, cells) == 0) { *slot_out = (int)m; return MG_OK; }
+    if ((int)e->map_grids.size() >= MG_MAX_MAPS) return fail(MG_ERR_ARG, "more than %d distinct large maps in one engine", MG_MAX_MAPS);
+    const int slot = (int)e->map_grids.size();
+    std::vector<int32_t> cidx(cells, -1), list;
+    for (int i = 0; i < s.H; i += s.gs)
+        for (int j = 0; j < s.W; j++)
+            if (!grid_pitched[(size_t)i * s.P + j] && cidx[(size_t)i * s.P + j] < 0) { cidx[(size_t)i * s.P + j] = (int)list.size(); list.push_back(i * s.P + j); }
+    for (int i = 0; i < s.H; i++)
+        for (int j = 0; j < s.W; j += s.gs)
+            if (!grid_pitched[(size_t)i * s.P + j] && cidx[(size_t)i * s.P + j] < 0) { cidx[(size_t)i * s.P + j] = (int)list.size(); list.push_back(i * s.P + j); }
+    const int K = (int)list.size();
+    uint16_t *pre = nullptr;
+    CU(dalloc(&pre, (size_t)std::max(K, 1) * std::max(K, 1)));
+    uint8_t *d_grid = nullptr, *scratch = nullptr;
+    int32_t *d_list = nullptr;
+    CU(dalloc(&d_grid, cells));
+    CU(dalloc(&d_list, (size_t)std::max(K, 1)));
+    CU(cudaMemcpy(d_grid, grid_pitched, cells, cudaMemcpyHostToDevice));
+    if (K > 0) {
+        CU(cudaMemcpy(d_list, list.data(), (size_t)K * 4, cudaMemcpyHostToDevice));
+        const int blocks = std::min(K, 2 * e->n_sms);
+        CU(dalloc(&scratch, (size_t)blocks * (cells * 10 + 64)));
+        e->launches++;
+        precompute_kernel<<<blocks, 256, 0, e->stream>>>(d_grid, s.H, s.W, s.P, d_list, K, pre, scratch);
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(scratch); cudaFree(d_grid); cudaFree(d_list);
+    CU(cudaMemcpy(s.cell_idx + (size_t)slot * cells, cidx.data(), cells * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.pre + slot, &pre, sizeof pre, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.preK + slot, &K, 4, cudaMemcpyHostToDevice));
+    e->map_grids.emplace_back(grid_pitched, grid_pitched + cells);
+    e->map_pre.push_back(pre);
+    *slot_out = slot;
+    return MG_OK;
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -433,8 +497,8 @@ static int make_window_maps(mg_engine *e)
     const EnvState &s = e->s;
     const cuuint32_t box[3] = {24, 11, 1}, estr[3] = {1, 1, 1};   // 24 cols: 8-aligned start + 11-wide window (see kernel)
     {   // cost-to-go fields: [E*N planes][H rows][P cols] u16
-        const cuuint64_t dims[3] = {(cuuint64_t)s.P, (cuuint64_t)s.H, (cuuint64_t)s.E * s.N};
-        const cuuint64_t strides[2] = {(cuuint64_t)s.P * 2, (cuuint64_t)s.H * s.P * 2};
+        const cuuint64_t dims[3] = {(cuuint64_t)s.FP, (cuuint64_t)s.FR, (cuuint64_t)s.E * s.N};
+        const cuuint64_t strides[2] = {(cuuint64_t)s.FP * 2, (cuuint64_t)s.FR * s.FP * 2};
         if (enc(&e->map_c2g, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, s.c2g, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return fail(MG_ERR_CUDA, "cuTensorMapEncodeTiled(c2g) failed");
@@ -569,11 +633,11 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
     }
     if (p.save_cost2go) { fail(MG_ERR_ARG, "save_cost2go (precomputed_cost2go.bin cache) is not implemented"); return nullptr; }
     if (max_envs < 1 || max_agents < 1 || max_agents > 32767) { fail(MG_ERR_ARG, "bad capacity"); return nullptr; }
-    if (H < 11 || W < 11 || H > 74 || W > 74) {
-        fail(MG_ERR_ARG, "padded grid %dx%d unsupported: need 11..74 per side (larger maps need the windowed "
-                         "cost-to-go machinery, observation_generator.cpp:200-286; not built yet)", H, W);
+    if (H < 11 || W < 11 || H > 512 || W > 512) {
+        fail(MG_ERR_ARG, "padded grid %dx%d unsupported: need 11..512 cells per side", H, W);
         return nullptr;
     }
+    if (p.grid_step != 64) { fail(MG_ERR_ARG, "grid_step must be 64 (inference.py:28)"); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         fail(MG_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -585,11 +649,22 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
     e->params = p;
     EnvState &s = e->s;
     s.E = max_envs; s.N = max_agents; s.H = H; s.W = W; s.P = (W + 7) / 8 * 8;
+    s.gs = p.grid_step;
+    // H, W <= 74: every agent's window is the whole grid and the field is one goal BFS; beyond that the
+    // windowed machinery of observation_generator.cpp:43-286 runs (precompute tables + per-agent partial fields)
+    s.large = (H > 74 || W > 74) ? 1 : 0;
+    s.FR = s.large ? 2 * s.gs + 1 : s.H;
+    s.FP = s.large ? (2 * s.gs + 1 + 7) / 8 * 8 : s.P;
     const size_t cells = (size_t)s.H * s.P, EN = (size_t)s.E * s.N;
     bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && dalloc(&s.obst, s.E * cells) == cudaSuccess;
     ok = ok && dalloc(&s.loc, s.E * cells) == cudaSuccess;
-    ok = ok && dalloc(&s.c2g, EN * cells) == cudaSuccess;
+    ok = ok && dalloc(&s.c2g, EN * s.FR * s.FP) == cudaSuccess && dalloc(&s.bounds, EN) == cudaSuccess;
+    ok = ok && dalloc(&s.map_of_env, (size_t)s.E) == cudaSuccess;
+    if (s.large) {
+        ok = ok && dalloc(&s.cell_idx, (size_t)MG_MAX_MAPS * cells) == cudaSuccess && dalloc(&s.pre, MG_MAX_MAPS) == cudaSuccess;
+        ok = ok && dalloc(&s.preK, MG_MAX_MAPS) == cudaSuccess;
+    }
     ok = ok && dalloc(&s.pos, EN) == cudaSuccess && dalloc(&s.goal, EN) == cudaSuccess;
     ok = ok && dalloc(&s.hist, EN * 8) == cudaSuccess && dalloc(&s.nextb, EN) == cudaSuccess;
     ok = ok && dalloc(&s.act, EN) == cudaSuccess && dalloc(&s.nag, (size_t)s.E) == cudaSuccess;
@@ -603,6 +678,7 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
     ok = ok && dalloc(&e->d_act_in, EN) == cudaSuccess && dalloc(&e->d_step_act, EN) == cudaSuccess;
     ok = ok && dalloc(&e->d_q, EN * 5) == cudaSuccess && dalloc(&e->d_metrics, (size_t)s.E * 8) == cudaSuccess;
     if (ok) {
+        cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
         cudaMemset(s.nag, 0, s.E * 4);
         cudaMemset(s.active, 1, s.E);
         cudaMemset(s.vocab_err, 0, 4);
@@ -614,7 +690,9 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
         cudaMemset(s.agent_steps, 0, s.E * 8);
         cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
         for (auto &ev : e->ev_p) cudaEventCreate(&ev);
-        cudaFuncSetAttribute(bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem(s));
+        if (s.large) cudaFuncSetAttribute(partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partial_smem(s));
+        else cudaFuncSetAttribute(bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfs_smem(s));
+        cudaMemset(s.map_of_env, 0, (size_t)s.E * 4);
         cudaFuncSetAttribute(sample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem(s));
         ok = cudaDeviceSynchronize() == cudaSuccess;
     }
@@ -642,6 +720,8 @@ void mg_engine_destroy(mg_engine *e)
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     EnvState &s = e->s;
+    for (auto p : e->map_pre) cudaFree(p);
+    cudaFree(s.bounds); cudaFree(s.map_of_env); cudaFree(s.cell_idx); cudaFree(s.pre); cudaFree(s.preK);
     cudaFree(s.obst); cudaFree(s.loc); cudaFree(s.c2g); cudaFree(s.pos); cudaFree(s.goal); cudaFree(s.hist);
     cudaFree(s.nextb); cudaFree(s.act); cudaFree(s.nag); cudaFree(s.dirty); cudaFree(s.tokens); cudaFree(s.logits);
     cudaFree(s.active); cudaFree(s.steps); cudaFree(s.done); cudaFree(s.arrive); cudaFree(s.agent_steps); cudaFree(s.vocab_err);
@@ -765,8 +845,14 @@ int mg_engine_reset(mg_engine *e, int first_env, int n_envs, int n_agents, const
             arrive[(size_t)k * s.N + a] = (p[0] == g[0] && p[1] == g[1]) ? 0 : -1;
         }
     }
-    std::vector<int32_t> nag(n_envs, n_agents);
+    std::vector<int32_t> nag(n_envs, n_agents), map_of(n_envs, 0);
+    if (s.large)
+        for (int k = 0; k < n_envs; k++) {
+            int rc = add_large_map(e, ob.data() + (size_t)k * cells, &map_of[k]);
+            if (rc) return rc;
+        }
     const size_t eo = (size_t)first_env;
+    CU(cudaMemcpyAsync(s.map_of_env + eo, map_of.data(), n_envs * 4, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(s.obst + eo * cells, ob.data(), ob.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(s.loc + eo * cells, loc.data(), loc.size() * 2, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(s.pos + eo * s.N, pos.data(), EN * sizeof(short2), cudaMemcpyHostToDevice, e->stream));
@@ -781,12 +867,8 @@ int mg_engine_reset(mg_engine *e, int first_env, int n_envs, int n_agents, const
     CU(cudaMemsetAsync(s.done + eo, 0, n_envs, e->stream));
     CU(cudaMemsetAsync(s.agent_steps + eo, 0, n_envs * 8, e->stream));
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
-    prof_begin(e, KC_BFS);
-    bfs_kernel<<<n_envs * s.N, 128, bfs_smem(s), e->stream>>>(s, first_env, 0);
-    prof_end(e);
-    CU(cudaGetLastError());
     e->n_envs = std::max(e->n_envs, first_env + n_envs);
-    return MG_OK;
+    return launch_fields(e, first_env, n_envs, 0);
 }
 
 int mg_engine_update_agents(mg_engine *e, const int32_t *pos_xy, const int32_t *goal_xy, const int32_t *actions)
@@ -804,10 +886,13 @@ int mg_engine_update_agents(mg_engine *e, const int32_t *pos_xy, const int32_t *
         set_state_kernel<<<e->n_envs, 256, 0, e->stream>>>(s, pos_xy ? e->d_pos_in : nullptr, goal_xy ? e->d_goal_in : nullptr,
                                                            actions ? e->d_act_in : nullptr);
     }
-    if (goal_xy) {  // changed goals -> recompute their fields (cpp:464-468,479-481)
-        prof_begin(e, KC_BFS);
-        bfs_kernel<<<e->n_envs * s.N, 128, bfs_smem(s), e->stream>>>(s, 0, 1);
-        prof_end(e);
+    if (s.large && !pos_xy && !goal_xy) {   // positions moved on the device (mg_engine_env_step) may have left their windows
+        int rc = launch_fields(e, 0, e->n_envs, 1);
+        if (rc) return rc;
+    }
+    if (goal_xy || (pos_xy && s.large)) {  // changed goals / FOV left the window -> recompute those fields (cpp:464-481)
+        int rc = launch_fields(e, 0, e->n_envs, 1);
+        if (rc) return rc;
     }
     return launch_observe(e, true, false);
 }
@@ -912,6 +997,7 @@ int mg_engine_rollout(mg_engine *e, int n_steps, int mode)
         int rc;
         const bool ph = e->profiling && t == n_steps - 1;
         if (ph) cudaEventRecord(e->ev_p[0], e->stream);
+        if (s.large && (rc = launch_fields(e, 0, e->n_envs, 1))) return rc;   // agents whose FOV left their window
         if ((rc = launch_observe(e, true, true))) return rc;
         if (ph) cudaEventRecord(e->ev_p[1], e->stream);
         if ((rc = forward_device(e, s.tokens, EN, s.logits))) return rc;
@@ -942,12 +1028,8 @@ int mg_engine_act_host(mg_engine *e, const int32_t *pos_xy, const int32_t *goal_
         set_state_kernel<<<e->n_envs, 256, 0, e->stream>>>(s, pos_xy ? e->d_pos_in : nullptr,
                                                            goal_xy ? e->d_goal_in : nullptr, nullptr);
     }
-    if (goal_xy) {
-        prof_begin(e, KC_BFS);
-        bfs_kernel<<<e->n_envs * s.N, 128, bfs_smem(s), e->stream>>>(s, 0, 1);
-        prof_end(e);
-    }
     int rc;
+    if ((goal_xy || (pos_xy && s.large)) && (rc = launch_fields(e, 0, e->n_envs, 1))) return rc;
     if ((rc = launch_observe(e, true, true))) return rc;
     if ((rc = forward_device(e, s.tokens, (int)EN, s.logits))) return rc;
     if ((rc = launch_step(e, mode, 0, e->d_q, nullptr))) return rc;
@@ -991,12 +1073,33 @@ int mg_engine_get_cost2go(mg_engine *e, int env, int agent, uint16_t *out_hw)
     EnvState &s = e->s;
     if (env < 0 || env >= e->n_envs || agent < 0 || agent >= s.N) return fail(MG_ERR_ARG, "index out of range");
     CU(cudaSetDevice(e->device));
+    if (s.large) return fail(MG_ERR_ARG, "large maps hold windowed fields: use mg_engine_get_partial");
     const size_t cells = (size_t)s.H * s.P;
     std::vector<uint16_t> t(cells);
     CU(cudaMemcpyAsync(t.data(), s.c2g + ((size_t)env * s.N + agent) * cells, cells * 2, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < s.H; i++) memcpy(out_hw + (size_t)i * s.W, t.data() + (size_t)i * s.P, s.W * 2);
     return MG_OK;
+}
+
+int mg_engine_get_partial(mg_engine *e, int env, int agent, int32_t *bounds4, uint16_t *out, int cap)
+{
+    if (!e || !bounds4) return fail(MG_ERR_ARG, "null argument");
+    EnvState &s = e->s;
+    if (env < 0 || env >= e->n_envs || agent < 0 || agent >= s.N) return fail(MG_ERR_ARG, "index out of range");
+    CU(cudaSetDevice(e->device));
+    short4 b;
+    CU(cudaMemcpyAsync(&b, s.bounds + (size_t)env * s.N + agent, sizeof b, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<uint16_t> t((size_t)s.FR * s.FP);
+    CU(cudaMemcpyAsync(t.data(), s.c2g + ((size_t)env * s.N + agent) * s.FR * s.FP, t.size() * 2, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    bounds4[0] = b.x; bounds4[1] = b.y; bounds4[2] = b.z; bounds4[3] = b.w;
+    const int rows = b.y - b.x + 1, cols = b.w - b.z + 1;
+    if (out) {
+        if (cap < rows * cols) return fail(MG_ERR_ARG, "buffer too small for a %dx%d window", rows, cols);
+        for (int i = 0; i < rows; i++) memcpy(out + (size_t)i * cols, t.data() + (size_t)i * s.FP, (size_t)cols * 2);
+    }
+    return rows * cols;
 }
 
 int mg_engine_get_metrics(mg_engine *e, double *out)

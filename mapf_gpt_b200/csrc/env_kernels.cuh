@@ -19,6 +19,15 @@ namespace mg {
 
 struct EnvState {
     int E, N, H, W, P;
+    int FR, FP;          // rows / pitch of one agent's cost-to-go field: (H, P) when the window is the whole grid
+                         // (H, W <= 74), else (129, 136) = two grid_step blocks + 1 (cpp:207-210)
+    int large;           // general windowed machinery on (some side > 74 cells)
+    int gs;              // grid_step (64)
+    short4 *bounds;      // [E][N] inclusive window (x=left, y=right, z=top, w=bottom), Cost2GoPartial h:67-82
+    int32_t *map_of_env; // [E] slot of the per-map precompute tables (large only)
+    int32_t *cell_idx;   // [maps][H*P] index of a precomputed cell or -1 (precomputed_cells_map, cpp:45-60)
+    uint16_t **pre;      // [maps] -> K x K all-pairs distances between precomputed cells (cpp:82-113)
+    int32_t *preK;       // [maps] K
     uint8_t *obst;
     int16_t *loc;
     uint16_t *c2g;
@@ -99,7 +108,246 @@ __global__ void __launch_bounds__(128) bfs_kernel(EnvState s, int first_env, int
     uint16_t *out = s.c2g + ((size_t)e * s.N + a) * cells;
     for (int i = threadIdx.x; i < cells / 2; i += blockDim.x)
         reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<uint32_t *>(dist)[i];
-    if (threadIdx.x == 0) s.dirty[e * s.N + a] = 0;
+    if (threadIdx.x == 0) {
+        s.dirty[e * s.N + a] = 0;
+        s.bounds[e * s.N + a] = make_short4(0, (short)(s.H - 1), 0, (short)(s.W - 1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// General cost-to-go machinery for maps wider than the window (some side > 74 cells), SURVEY 8(f).1.
+//
+// precompute_kernel: precompute_cost2go (cpp:43-113): one full-grid BFS per precomputed cell (free cells on rows/cols
+// = 0 mod grid_step); pre[a][b] = distance between precomputed cells a and b.  Persistent blocks, each with its own
+// global scratch (dist u16 + two u32 queues), level-synchronous.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) precompute_kernel(const uint8_t *__restrict__ obst, int H, int W, int P,
+                                                         const int32_t *__restrict__ cells_list, int K,
+                                                         uint16_t *__restrict__ pre, uint8_t *scratch)
+{
+    const int cells = H * P;
+    uint16_t *dist = reinterpret_cast<uint16_t *>(scratch + (size_t)blockIdx.x * ((size_t)cells * 10 + 64));
+    uint32_t *q0 = reinterpret_cast<uint32_t *>(dist + cells + (cells & 1));
+    uint32_t *q1 = q0 + cells;
+    __shared__ int n_next;
+    for (int a = blockIdx.x; a < K; a += gridDim.x) {
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) dist[i] = 0xFFFF;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            dist[cells_list[a]] = 0;
+            q0[0] = (uint32_t)cells_list[a];
+            n_next = 0;
+        }
+        __syncthreads();
+        int n_cur = 1, level = 0;
+        uint32_t *qc = q0, *qn = q1;
+        while (n_cur > 0) {
+            for (int i = threadIdx.x; i < n_cur; i += blockDim.x) {
+                const int c = (int)qc[i];
+                const int ci = c / P, cj = c - ci * P;
+#pragma unroll
+                for (int m = 1; m < 5; m++) {
+                    const int ni = ci + c_moves[m][0], nj = cj + c_moves[m][1];
+                    if (ni < 0 || nj < 0 || ni >= H || nj >= W) continue;
+                    const int nc = ni * P + nj;
+                    if (obst[nc]) continue;
+                    if (atomicCAS(reinterpret_cast<unsigned short *>(&dist[nc]), (unsigned short)0xFFFF,
+                                  (unsigned short)(level + 1)) == 0xFFFF)
+                        qn[atomicAdd(&n_next, 1)] = (uint32_t)nc;
+                }
+            }
+            __syncthreads();
+            n_cur = n_next;
+            __syncthreads();
+            if (threadIdx.x == 0) n_next = 0;
+            uint32_t *t = qc; qc = qn; qn = t;
+            level++;
+            __syncthreads();
+        }
+        for (int b = threadIdx.x; b < K; b += blockDim.x) pre[(size_t)a * K + b] = dist[cells_list[b]];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// partial_kernel: compute_cost2go_partial (cpp:200-286) for one (env, agent) per block:
+//   window = two grid_step blocks from the block holding pos-5, clipped (cpp:207-210);
+//   goal-block BFS (get_goal_border_and_cost2go, cpp:134-176);
+//   seeds on the window border lines: min over goal-block border cells of gcm[g] + pre[g][cell] (cpp:224-239), plus the
+//   goal itself when it lies inside the window (cpp:241-245);
+//   multi-source BFS over the window with seeds injected when the frontier reaches their cost (cpp:246-279).  The
+//   reference's FIFO is reproduced level by level: all seeds of cost c are injected before level c expands -- and, as in
+//   the reference (cpp:259,276), an injected seed OVERWRITES a smaller cost already on its cell.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) partial_kernel(EnvState s, int first_env, int only_dirty)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int e = first_env + blockIdx.x / s.N, a = blockIdx.x % s.N;
+    if (a >= s.nag[e]) return;
+    const int idx = e * s.N + a;
+    if (only_dirty && !s.dirty[idx]) return;
+    const int H = s.H, W = s.W, P = s.P, gs = s.gs;
+    const int WMAX = 2 * gs + 1;                       // 129
+    const int QCAP = WMAX * WMAX + 4 * WMAX + 8;       // every window cell once + re-pushed seeds
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { uint8_t *p = sm + off; off += (bytes + 15) & ~(size_t)15; return p; };
+    uint16_t *cm = reinterpret_cast<uint16_t *>(carve((size_t)WMAX * WMAX * 2));           // window cost matrix
+    uint16_t *gcm = reinterpret_cast<uint16_t *>(carve((size_t)(gs + 1) * (gs + 1) * 2));  // goal-block cost matrix
+    uint16_t *q0 = reinterpret_cast<uint16_t *>(carve((size_t)QCAP * 2));                  // frontier queues (window-local ids)
+    uint16_t *q1 = reinterpret_cast<uint16_t *>(carve((size_t)QCAP * 2));
+    int *seed_cost = reinterpret_cast<int *>(carve((size_t)(4 * WMAX + 4) * 4));
+    uint16_t *seed_cell = reinterpret_cast<uint16_t *>(carve((size_t)(4 * WMAX + 4) * 2));
+    __shared__ int n_next, n_seeds, next_cost;
+
+    const uint8_t *ob = s.obst + (size_t)e * H * P;
+    const short2 pos = s.pos[idx], goal = s.goal[idx];
+    const int left = max(pos.x - 5, 0) / gs * gs, right = min(left + 2 * gs, H - 1);
+    const int top = max(pos.y - 5, 0) / gs * gs, bottom = min(top + 2 * gs, W - 1);
+    const int wr = right - left + 1, wc = bottom - top + 1;
+    const int gL = goal.x / gs * gs, gR = min(gL + gs, H - 1), gT = goal.y / gs * gs, gB = min(gT + gs, W - 1);
+    const int gc = gB - gT + 1, gr = gR - gL + 1;
+
+    // ---- goal-block BFS
+    for (int i = threadIdx.x; i < gr * gc; i += blockDim.x) gcm[i] = 0xFFFF;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gcm[(goal.x - gL) * gc + (goal.y - gT)] = 0;
+        q0[0] = (uint16_t)((goal.x - gL) * gc + (goal.y - gT));
+        n_next = 0;
+    }
+    __syncthreads();
+    {
+        int n_cur = 1, level = 0;
+        uint16_t *qc = q0, *qn = q1;
+        while (n_cur > 0) {
+            for (int i = threadIdx.x; i < n_cur; i += blockDim.x) {
+                const int c = qc[i];
+                const int ci = c / gc + gL, cj = c % gc + gT;
+#pragma unroll
+                for (int m = 1; m < 5; m++) {
+                    const int ni = ci + c_moves[m][0], nj = cj + c_moves[m][1];
+                    if (ni < gL || nj < gT || ni > gR || nj > gB) continue;
+                    if (ob[ni * P + nj]) continue;
+                    const int nc = (ni - gL) * gc + (nj - gT);
+                    if (atomicCAS(reinterpret_cast<unsigned short *>(&gcm[nc]), (unsigned short)0xFFFF,
+                                  (unsigned short)(level + 1)) == 0xFFFF)
+                        qn[atomicAdd(&n_next, 1)] = (uint16_t)nc;
+                }
+            }
+            __syncthreads();
+            n_cur = n_next;
+            __syncthreads();
+            if (threadIdx.x == 0) n_next = 0;
+            uint16_t *t = qc; qc = qn; qn = t;
+            level++;
+            __syncthreads();
+        }
+    }
+    // ---- seeds on the window border lines (get_cells_on_border, cpp:178-198: unclipped far lines, only if inside the grid)
+    const int map = s.map_of_env[e];
+    const int32_t *cidx = s.cell_idx + (size_t)map * H * P;
+    const uint16_t *pre = s.pre[map];
+    const int K = s.preK[map];
+    const int far_r = left + 2 * gs, far_c = top + 2 * gs;
+    const int n_i = min(far_r, H) - left, n_j = min(far_c, W) - top;
+    if (threadIdx.x == 0) n_seeds = 0;
+    for (int i = threadIdx.x; i < wr * wc; i += blockDim.x) cm[i] = 0xFFFF;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * n_i + 2 * n_j; t += blockDim.x) {
+        int ci, cj;
+        if (t < n_i) { ci = left + t; cj = top; }
+        else if (t < 2 * n_i) { if (far_c >= W) continue; ci = left + (t - n_i); cj = far_c; }
+        else if (t < 2 * n_i + n_j) { ci = left; cj = top + (t - 2 * n_i); }
+        else { if (far_r >= H) continue; ci = far_r; cj = top + (t - 2 * n_i - n_j); }
+        if (ob[ci * P + cj]) continue;
+        const int ccol = cidx[ci * P + cj];
+        int min_cost = 65535;
+        // goal-block border cells (cpp:141-152)
+        for (int u = 0; u < 2 * gr + 2 * gc; u++) {
+            int gi, gj;
+            if (u < gr) { gi = gL + u; gj = gT; }
+            else if (u < 2 * gr) { if (gT + gs >= W) continue; gi = gL + (u - gr); gj = gB; }
+            else if (u < 2 * gr + gc) { gi = gL; gj = gT + (u - 2 * gr); }
+            else { if (gL + gs >= H) continue; gi = gR; gj = gT + (u - 2 * gr - gc); }
+            if (ob[gi * P + gj]) continue;
+            const int gcost = gcm[(gi - gL) * gc + (gj - gT)];
+            if (gcost == 0xFFFF) continue;
+            const int nc = gcost + (int)pre[(size_t)cidx[gi * P + gj] * K + ccol];
+            if (min_cost > nc) min_cost = nc;
+        }
+        if (min_cost != 65535) {
+            const int k = atomicAdd(&n_seeds, 1);
+            seed_cost[k] = min_cost;
+            seed_cell[k] = (uint16_t)((ci - left) * wc + (cj - top));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && goal.x >= left && goal.x <= right && goal.y >= top && goal.y <= bottom) {
+        const int k = n_seeds++;
+        seed_cost[k] = 0;
+        seed_cell[k] = (uint16_t)((goal.x - left) * wc + (goal.y - top));
+    }
+    __syncthreads();
+    // ---- multi-source BFS, level by level
+    const int ns = n_seeds;
+    {
+        int n_cur = 0, c = 0;
+        uint16_t *qc = q0, *qn = q1;
+        while (true) {
+            if (n_cur == 0) {   // fringe empty: jump to the cheapest pending seed (cpp:247-249, 273-278); seeds < c are done
+                if (threadIdx.x == 0) next_cost = 0x7FFFFFFF;
+                __syncthreads();
+                int best = 0x7FFFFFFF;
+                for (int k = threadIdx.x; k < ns; k += blockDim.x)
+                    if (seed_cost[k] >= c) best = min(best, seed_cost[k]);
+                if (best != 0x7FFFFFFF) atomicMin(&next_cost, best);
+                __syncthreads();
+                if (next_cost == 0x7FFFFFFF) break;
+                c = next_cost;
+                if (threadIdx.x == 0) n_next = 0;
+                __syncthreads();
+            }
+            // inject the seeds of cost c (overwriting, cpp:259,276)
+            if (threadIdx.x == 0) n_next = n_cur;
+            __syncthreads();
+            for (int k = threadIdx.x; k < ns; k += blockDim.x)
+                if (seed_cost[k] == c) {
+                    cm[seed_cell[k]] = (uint16_t)c;
+                    qc[atomicAdd(&n_next, 1)] = seed_cell[k];
+                }
+            __syncthreads();
+            n_cur = n_next;
+            __syncthreads();
+            if (threadIdx.x == 0) n_next = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_cur; i += blockDim.x) {
+                const int cell = qc[i];
+                const int ci = cell / wc + left, cj = cell % wc + top;
+#pragma unroll
+                for (int m = 1; m < 5; m++) {
+                    const int ni = ci + c_moves[m][0], nj = cj + c_moves[m][1];
+                    if (ni < left || ni > right || nj < top || nj > bottom) continue;
+                    if (ob[ni * P + nj]) continue;
+                    const int nc = (ni - left) * wc + (nj - top);
+                    if (atomicCAS(reinterpret_cast<unsigned short *>(&cm[nc]), (unsigned short)0xFFFF,
+                                  (unsigned short)(c + 1)) == 0xFFFF)
+                        qn[atomicAdd(&n_next, 1)] = (uint16_t)nc;
+                }
+            }
+            __syncthreads();
+            n_cur = n_next;
+            __syncthreads();
+            uint16_t *t = qc; qc = qn; qn = t;
+            c++;
+        }
+    }
+    // ---- store the partial field and its window
+    uint16_t *out = s.c2g + (size_t)idx * s.FR * s.FP;
+    for (int i = threadIdx.x; i < wr * wc; i += blockDim.x) out[(i / wc) * s.FP + (i % wc)] = cm[i];
+    if (threadIdx.x == 0) {
+        s.bounds[idx] = make_short4((short)left, (short)right, (short)top, (short)bottom);
+        s.dirty[idx] = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -142,6 +390,14 @@ __global__ void __launch_bounds__(256) set_state_kernel(EnvState s, const int32_
             }
         }
     }
+    if (pos_in && s.large) {   // FOV leaves the window -> recompute the partial field (cpp:469-477)
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const short2 p = s.pos[e * s.N + i];
+            const short4 b = s.bounds[e * s.N + i];
+            if (p.x - 5 < b.x || p.x + 5 > b.y || p.y - 5 < b.z || p.y + 5 > b.w) s.dirty[e * s.N + i] = 1;
+        }
+    }
     if (act_in) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) s.act[e * s.N + i] = act_in[e * s.N + i];
     }
@@ -154,10 +410,10 @@ __global__ void __launch_bounds__(256) set_state_kernel(EnvState s, const int32_
 //                      (cpp:487-514), Encoder::encode (cpp:352-389) -> 256 uint8 tokens per agent.
 // Trained shape only: radius 5, 13 agents, 5 previous actions, limit 20, context 256.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int field_dist(const uint16_t *F, int x, int y, int H, int W, int P)
-{   // get_distance, cpp:313-319: window = [0,H-1] x [0,W-1], upper bounds EXCLUSIVE
-    if (x < 0 || x >= H - 1 || y < 0 || y >= W - 1) return -1;
-    return F[x * P + y];
+__device__ __forceinline__ int field_dist(const uint16_t *F, int x, int y, const short4 b, int FP)
+{   // get_distance, cpp:313-319: -1 outside [left,right) x [top,bottom) -- upper bounds EXCLUSIVE
+    if (x < b.x || x >= b.y || y < b.z || y >= b.w) return -1;
+    return F[(x - b.x) * FP + (y - b.z)];
 }
 
 template <bool kUpdate, bool kTokens>
@@ -178,13 +434,14 @@ __global__ void __launch_bounds__(256) observe_kernel(EnvState s)
             uint8_t *h = s.hist + (size_t)idx * 8;
             h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = h[4];
             h[4] = (a >= 0 && a <= 4) ? (uint8_t)(45 + a) : (uint8_t)44;
-            const uint16_t *F = s.c2g + (size_t)idx * cells;
+            const uint16_t *F = s.c2g + (size_t)idx * s.FR * s.FP;
             const short2 p = s.pos[idx];
-            const int cur = field_dist(F, p.x, p.y, s.H, s.W, s.P);
+            const short4 bd = s.bounds[idx];
+            const int cur = field_dist(F, p.x, p.y, bd, s.FP);
             int bits = 0;
 #pragma unroll
             for (int m = 1; m < 5; m++) {
-                const int nb = field_dist(F, p.x + c_moves[m][0], p.y + c_moves[m][1], s.H, s.W, s.P);
+                const int nb = field_dist(F, p.x + c_moves[m][0], p.y + c_moves[m][1], bd, s.FP);
                 bits = (bits << 1) | ((nb >= 0 && cur > nb) ? 1 : 0);
             }
             s.nextb[idx] = (uint8_t)bits;
@@ -196,9 +453,10 @@ __global__ void __launch_bounds__(256) observe_kernel(EnvState s)
     const int16_t *loc = s.loc + (size_t)e * cells;
     for (int i = warp; i < n; i += (blockDim.x >> 5)) {
         const int idx = e * s.N + i;
-        const uint16_t *F = s.c2g + (size_t)idx * cells;
         const short2 p = s.pos[idx];
-        const int mid = F[p.x * s.P + p.y];
+        const short4 bd = s.bounds[idx];
+        const uint16_t *F = s.c2g + (size_t)idx * s.FR * s.FP + (p.x - 5 - bd.x) * s.FP + (p.y - 5 - bd.z);   // window origin
+        const int mid = F[5 * s.FP + 5];
         uint8_t *tb = tokbuf[warp];
         unsigned key[4];
 #pragma unroll
@@ -208,7 +466,7 @@ __global__ void __launch_bounds__(256) observe_kernel(EnvState s)
             if (w < 121) {
                 const int wi = w / 11, wj = w - wi * 11;
                 const int c = (p.x - 5 + wi) * s.P + (p.y - 5 + wj);
-                const int v = F[c];
+                const int v = F[wi * s.FP + wj];
                 int tok;
                 if (v == 0xFFFF) tok = 41;
                 else {
@@ -280,7 +538,6 @@ __global__ void __launch_bounds__(256) observe_tma_kernel(EnvState s, const __gr
     const int e = blockIdx.x;
     const int n = s.nag[e];
     if (n == 0 || !s.active[e]) return;
-    const int cells = s.H * s.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ __align__(128) uint16_t win[8][2][2][320];   // [warp][buffer][field: 0 c2g, 1 loc][11 rows x 24 cols], 640-byte blocks (128-byte aligned TMA destinations)
     __shared__ __align__(16) uint8_t tokbuf[8][256];
@@ -299,13 +556,14 @@ __global__ void __launch_bounds__(256) observe_tma_kernel(EnvState s, const __gr
             uint8_t *h = s.hist + (size_t)idx * 8;
             h[0] = h[1]; h[1] = h[2]; h[2] = h[3]; h[3] = h[4];
             h[4] = (a >= 0 && a <= 4) ? (uint8_t)(45 + a) : (uint8_t)44;
-            const uint16_t *F = s.c2g + (size_t)idx * cells;
+            const uint16_t *F = s.c2g + (size_t)idx * s.FR * s.FP;
             const short2 p = s.pos[idx];
-            const int cur = field_dist(F, p.x, p.y, s.H, s.W, s.P);
+            const short4 bd = s.bounds[idx];
+            const int cur = field_dist(F, p.x, p.y, bd, s.FP);
             int bits = 0;
 #pragma unroll
             for (int m = 1; m < 5; m++) {
-                const int nb = field_dist(F, p.x + c_moves[m][0], p.y + c_moves[m][1], s.H, s.W, s.P);
+                const int nb = field_dist(F, p.x + c_moves[m][0], p.y + c_moves[m][1], bd, s.FP);
                 bits = (bits << 1) | ((nb >= 0 && cur > nb) ? 1 : 0);
             }
             s.nextb[idx] = (uint8_t)bits;
@@ -316,8 +574,9 @@ __global__ void __launch_bounds__(256) observe_tma_kernel(EnvState s, const __gr
     auto issue = [&](int i, int buf) {
         if (lane == 0) {
             const short2 p = s.pos[e * s.N + i];
+            const short4 bd = s.bounds[e * s.N + i];
             mbar_expect_tx(&bars[warp][buf], 2 * 11 * 24 * 2);
-            tma_load_3d(&win[warp][buf][0][0], &map_c2g, (p.y - 5) & ~7, p.x - 5, e * s.N + i, &bars[warp][buf]);
+            tma_load_3d(&win[warp][buf][0][0], &map_c2g, (p.y - 5 - bd.z) & ~7, p.x - 5 - bd.x, e * s.N + i, &bars[warp][buf]);
             tma_load_3d(&win[warp][buf][1][0], &map_loc, (p.y - 5) & ~7, p.x - 5, e, &bars[warp][buf]);
         }
     };
@@ -330,9 +589,9 @@ __global__ void __launch_bounds__(256) observe_tma_kernel(EnvState s, const __gr
         mbar_wait(&bars[warp][buf], (it >> 1) & 1);
         const int idx = e * s.N + i;
         const short2 p = s.pos[idx];
-        const int lead = (p.y - 5) & 7;      // window column 0 inside the 8-aligned box
-        const uint16_t *wc = &win[warp][buf][0][0] + lead;
-        const int16_t *wl = reinterpret_cast<const int16_t *>(&win[warp][buf][1][0]) + lead;
+        const short4 bd = s.bounds[idx];
+        const uint16_t *wc = &win[warp][buf][0][0] + ((p.y - 5 - bd.z) & 7);      // window column 0 inside the 8-aligned box
+        const int16_t *wl = reinterpret_cast<const int16_t *>(&win[warp][buf][1][0]) + ((p.y - 5) & 7);
         const int mid = wc[5 * 24 + 5];
         uint8_t *tb = tokbuf[warp];
         unsigned key[4];
@@ -438,8 +697,7 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
     const int n = s.nag[e];
     if (n == 0 || !s.active[e]) return;
     const int cells = s.H * s.P;
-    int *claim = reinterpret_cast<int *>(sm);                 // [cells]
-    int *tgt = claim + cells;                                 // [N]
+    int *tgt = reinterpret_cast<int *>(sm);                   // [N]
     uint8_t *wait = reinterpret_cast<uint8_t *>(tgt + s.N);   // [N]
     int16_t *loc = s.loc + (size_t)e * cells;
     const uint8_t *ob = s.obst + (size_t)e * cells;
@@ -480,7 +738,6 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
     __syncthreads();
 
     // ---- soft collision step
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) claim[i] = 0x7FFFFFFF;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int idx = e * s.N + i;
         int act = a.act_override ? a.act_override[idx] : s.act[idx];
@@ -498,13 +755,18 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
         if (j >= 0 && j != i && tgt[j] == p.x * s.P + p.y) wait[i] = 2;  // mark; applied after the sweep
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
         if (wait[i] == 2) wait[i] = 1;
-        if (!wait[i]) atomicMin(&claim[tgt[i]], i);        // (c) lowest-index mover keeps the claim
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {    // (c) lowest-index mover keeps the claim (n <= 512: plain scan)
+        if (wait[i]) continue;
+        bool lose = false;
+        for (int j = 0; j < i; j++) lose |= (wait[j] != 1 && tgt[j] == tgt[i]);   // 0 or 3: a mover after (a),(b)
+        if (lose) wait[i] = 3;                              // applied after the sweep: losers must still block higher ids
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x)
-        if (!wait[i] && claim[tgt[i]] != i) wait[i] = 1;
+        if (wait[i] == 3) wait[i] = 1;
     // (d) followers of a blocked occupant, to the fixed point
     while (true) {
         __syncthreads();
@@ -532,6 +794,10 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
             p = make_short2((short)(t / s.P), (short)(t % s.P));
             s.pos[idx] = p;
             loc[t] = (int16_t)i;
+        }
+        if (s.large) {
+            const short4 b = s.bounds[idx];
+            if (p.x - 5 < b.x || p.x + 5 > b.y || p.y - 5 < b.z || p.y + 5 > b.w) s.dirty[idx] = 1;
         }
         const short2 g = s.goal[idx];
         const bool og = (p.x == g.x && p.y == g.y);

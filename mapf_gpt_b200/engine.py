@@ -175,6 +175,19 @@ class RolloutEngine:
         _lib.check(self._L.mg_engine_get_cost2go(self._h, env, agent, _ptr(out)))
         return out
 
+    def partial(self, env: int, agent: int):
+        """((left, right, top, bottom), field[rows, cols]) of one agent's cost-to-go window."""
+        b = np.zeros(4, dtype=np.int32)
+        n = self._L.mg_engine_get_partial(self._h, env, agent, _ptr(b), None, 0)
+        if n < 0:
+            _lib.check(n)
+        buf = np.empty(n, dtype=np.uint16)
+        n2 = self._L.mg_engine_get_partial(self._h, env, agent, _ptr(b), _ptr(buf), n)
+        if n2 < 0:
+            _lib.check(n2)
+        left, right, top, bottom = (int(v) for v in b)
+        return (left, right, top, bottom), buf.reshape(right - left + 1, bottom - top + 1)
+
     def metrics(self) -> np.ndarray:
         """[num_envs, 8]: ep_length, CSR, ISR, SoC, makespan, on_goal_now, agent_steps, n_agents"""
         out = np.empty((self.num_envs, 8), dtype=np.float64)

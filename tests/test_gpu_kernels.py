@@ -215,3 +215,104 @@ def test_fused_and_generic_paths_agree(dev, name, monkeypatch):
     from oracle import gpt_oracle as G
     ref = G.forward_logits(sd, cfg.n_layer, cfg.n_head, torch.from_numpy(toks.astype(np.int64)))[:, :5].numpy()
     assert np.abs(outs[0] - ref).max() < LOGIT_TOL and np.abs(outs[1] - ref).max() < LOGIT_TOL
+
+
+# ------------------------------------------------------------------------------------------------ large maps
+def _big_grid(seed=0, h=150, w=170, p=0.18):
+    from mapf_gpt_b200 import maps
+    rng = np.random.default_rng(seed)
+    return maps.pad_grid((rng.random((h, w)) < p).astype(np.uint8))
+
+
+def test_large_map_known_answer_main_scenario(dev, built):
+    """The reference's int main() (observation_generator.cpp:530-544): 256x256 free grid, agent (120,120), goal (20,200),
+    through the single-env C-ABI twin.  Exercises precompute tables + windowed partial fields on the GPU."""
+    import ctypes as C, hashlib
+    p = lambda a: np.ascontiguousarray(a, np.int32).ctypes.data_as(C.c_void_p)
+    grid = np.zeros((256, 256), np.int32)
+    h = built.mg_gen_create(p(grid), 256, 256, None)
+    assert h, built.mg_last_error()
+    pos, goal, act = np.array([[120, 120]], np.int32), np.array([[20, 200]], np.int32), np.array([0], np.int32)
+    assert built.mg_gen_create_agents(h, p(pos), p(goal), 1) == 0, built.mg_last_error()
+    assert built.mg_gen_update_agents(h, p(pos), p(goal), p(act), 1) == 0
+    out = np.empty((1, 256), np.int32)
+    assert built.mg_gen_generate_observations(h, out.ctypes.data_as(C.c_void_p)) == 0
+    built.mg_gen_destroy(h)
+    assert hashlib.sha256(out[0].astype(np.int8).tobytes()).hexdigest() == \
+        "896eb85aa89a369759917e5903f237dc28387e6b7d431fbd6703f302a97585e1"
+    assert (out[0] == GOLD_OBS["main_row"]).all()
+
+
+def test_large_map_windows_tokens_and_recompute_triggers(dev):
+    """160x180 random grid: partial fields (bounds + values) and tokens vs the C oracle while agents move across window
+    boundaries and goals change (cpp:200-286, 464-481)."""
+    import oracle
+    from mapf_gpt_b200 import engine as E, maps
+    grid = _big_grid()
+    m = {"name": "big", "grid": grid, "starts": np.zeros(grid.shape, bool), "goals": np.zeros(grid.shape, bool)}
+    n, envs = 48, 2
+    inst = [maps.sample_instance(m, n, 5, e) for e in range(envs)]
+    st, gl = np.stack([i[0] for i in inst]), np.stack([i[1] for i in inst])
+    eng = E.RolloutEngine(envs, n, *grid.shape)
+    eng.reset(0, grid, st, gl)
+    orc = [oracle.ObsOracle(grid) for _ in range(envs)]
+    for e in range(envs):
+        orc[e].create_agents(st[e], gl[e])
+        for a in range(0, n, 7):
+            b, f = eng.partial(e, a)
+            ob, of = orc[e].partial(a)
+            assert b == ob and (f == of).all(), (e, a, b, ob)
+    rng = np.random.default_rng(1)
+    free = np.argwhere(maps.largest_component(grid))
+    pos, act = st.copy(), np.full((envs, n), -1, np.int32)
+    for t in range(40):
+        if t % 9 == 4:
+            gl = gl.copy()
+            idx = rng.integers(0, n, 6)
+            gl[:, idx] = free[rng.integers(0, len(free), (envs, 6))]
+        eng.update_agents(pos, gl, act)
+        toks = eng.generate_observations()
+        for e in range(envs):
+            orc[e].update_agents(pos[e], gl[e], act[e])
+            assert (toks[e] == orc[e].generate_observations()).all(), f"step {t} env {e}"
+        # drift everybody the same way so that FOVs cross the 64-cell window lines
+        act = np.where(rng.random((envs, n)) < 0.7, 4 if t < 20 else 2, rng.integers(0, 5, (envs, n))).astype(np.int32)
+        newpos = eng.env_step(act)
+        for e in range(envs):
+            pos[e], _ = oracle.pogema_step_soft(grid, pos[e], act[e])
+        assert (newpos == pos).all()
+    for e in range(envs):
+        for a in range(0, n, 5):
+            b, f = eng.partial(e, a)
+            ob, of = orc[e].partial(a)
+            assert b == ob and (f == of).all()
+    eng.close()
+
+
+def test_large_map_device_rollout(dev):
+    """Device-resident rollout on a large grid: the per-step window trigger + partial recompute keep tokens exact."""
+    import oracle
+    from mapf_gpt_b200 import engine as E, maps, weights as W
+    grid = _big_grid(3, 120, 200)
+    m = {"name": "big", "grid": grid, "starts": np.zeros(grid.shape, bool), "goals": np.zeros(grid.shape, bool)}
+    n = 40
+    st, gl = maps.sample_instance(m, n, 2)
+    cfg = W.model_config("2M")
+    eng = E.RolloutEngine(1, n, *grid.shape)
+    eng.load_model(W.scale_weights(W.random_init(cfg), 3.0), cfg)
+    eng.reset(0, grid, st, gl)
+    eng.rollout(12, E.MODE_PHILOX)
+    pos = eng.positions()[0]
+    assert (grid[pos[:, 0], pos[:, 1]] == 0).all() and len({tuple(p) for p in pos.tolist()}) == n
+    # one more observe on the device, rebuilt on the CPU from the device's own positions (history masked)
+    eng.update_agents()
+    tok = eng.generate_observations()[0].astype(np.int32)
+    o = oracle.ObsOracle(grid)
+    o.create_agents(pos, gl)
+    o.update_agents(pos, gl, np.full(n, -1, np.int32))
+    ref = o.generate_observations()
+    for s_ in range(13):
+        tok[:, 125 + 10 * s_:130 + 10 * s_] = 0
+        ref[:, 125 + 10 * s_:130 + 10 * s_] = 0
+    assert (tok == ref).all()
+    eng.close()

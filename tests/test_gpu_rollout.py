@@ -139,7 +139,7 @@ def test_ragged_slots_and_edge_cases(built):
     with pytest.raises(_lib.MgError):
         eng.reset(0, grid, np.array([[[0, 0]]], np.int32), np.array([[[6, 6]]], np.int32))   # outside the padding contract
     with pytest.raises(_lib.MgError):
-        E.RolloutEngine(1, 4, 200, 200)                      # larger maps: not built yet
+        E.RolloutEngine(1, 4, 600, 600)                      # beyond the engine's grid capacity
     eng.close()
 
 
