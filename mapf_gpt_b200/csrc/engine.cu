@@ -290,8 +290,29 @@ static int launch_attn_hs(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream
     CU(cudaGetLastError());
     return MG_OK;
 }
+static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream_t st)
+{
+    constexpr int smem = attn_persistent_smem_bytes();
+    static bool attr_set = false;
+    static int n_sms = 148;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(attn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    const int n_items = n_seq * a.n_head;
+    if (e) prof_begin(e, KC_ATTN);
+    attn_persistent_kernel<<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(a, n_items);
+    if (e) prof_end(e);
+    CU(cudaGetLastError());
+    return MG_OK;
+}
 static int launch_attn(mg_engine *e, const AttnArgs &a, int hs, int n_seq, cudaStream_t st)
 {
+    static const bool classic = getenv("MAPF_GPT_B200_ATTN_CLASSIC") != nullptr;
+    if (hs == 32 && !classic) return launch_attn_persistent(e, a, n_seq, st);
     if (hs == 32) return launch_attn_hs<32>(e, a, n_seq, st);
     if (hs == 64) return launch_attn_hs<64>(e, a, n_seq, st);
     return fail(MG_ERR_ARG, "attention: head size %d unsupported (32 or 64)", hs);
@@ -558,7 +579,7 @@ static int check_vocab(mg_engine *e)
 // Pure UMMA issue/execute rate: operands stay in smem (zero-filled), one thread issues `iters` x 4 UMMAs (M128 x N x K16,
 // SS operands, no-swizzle K-major), then commits; out[0] = clock64 cycles from first issue to completion.
 template <int N>
-__global__ void __launch_bounds__(128) umma_rate_kernel(int iters, long long *out)
+__global__ void __launch_bounds__(128) umma_rate_kernel(int iters, long long *out, int ts)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *As = smem;                       // 4 k-steps: [8 kc][128][16B] = 16 KB
@@ -579,8 +600,10 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int iters, long long *ou
         const long long t0 = clock64();
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)
-                umma_ss(tmem, umma_desc(a + ks * 4096, 2048, 128), umma_desc(b + ks * 2 * N * 16, N * 16, 128), idesc, 1u);
+            for (int ks = 0; ks < 4; ks++) {
+                if (ts) umma_ts(tmem, tmem + 256 - 32 + ks * 8, umma_desc(b + ks * 2 * N * 16, N * 16, 128), idesc, 1u);   // A in TMEM
+                else umma_ss(tmem, umma_desc(a + ks * 4096, 2048, 128), umma_desc(b + ks * 2 * N * 16, N * 16, 128), idesc, 1u);
+            }
         }
         const long long t1 = clock64();
         umma_commit(&bar);
@@ -593,11 +616,11 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int iters, long long *ou
     if (threadIdx.x < 32) tmem_dealloc<256>(tmem);
 }
 template <int N>
-static int run_umma_rate(int iters, int ctas, long long *d_out, long long *h_out)
+static int run_umma_rate(int iters, int ctas, long long *d_out, long long *h_out, int ts)
 {
     const int smem = 16384 + 8 * N * 16;
     CU(cudaFuncSetAttribute(umma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    umma_rate_kernel<N><<<ctas, 128, smem>>>(iters, d_out);
+    umma_rate_kernel<N><<<ctas, 128, smem>>>(iters, d_out, ts);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h_out, d_out, 16, cudaMemcpyDeviceToHost));
     return MG_OK;
@@ -1259,11 +1282,13 @@ int mg_test_umma_rate(int device, int N, int iters, int ctas, long long *cycles2
     long long *d = nullptr;
     CU(dalloc(&d, 2));
     int rc = MG_ERR_ARG;
-    if (N == 48) rc = run_umma_rate<48>(iters, ctas, d, cycles2);
-    else if (N == 80) rc = run_umma_rate<80>(iters, ctas, d, cycles2);
-    else if (N == 128) rc = run_umma_rate<128>(iters, ctas, d, cycles2);
-    else if (N == 160) rc = run_umma_rate<160>(iters, ctas, d, cycles2);
-    else if (N == 256) rc = run_umma_rate<256>(iters, ctas, d, cycles2);
+    const int ts = N >= 1000;   // N + 1000: A operand from tensor memory (TS form), N <= 160
+    if (ts) N -= 1000;
+    if (N == 48) rc = run_umma_rate<48>(iters, ctas, d, cycles2, ts);
+    else if (N == 80) rc = run_umma_rate<80>(iters, ctas, d, cycles2, ts);
+    else if (N == 128) rc = run_umma_rate<128>(iters, ctas, d, cycles2, ts);
+    else if (N == 160) rc = run_umma_rate<160>(iters, ctas, d, cycles2, ts);
+    else if (N == 256 && !ts) rc = run_umma_rate<256>(iters, ctas, d, cycles2, ts);
     cudaFree(d);
     return rc;
 }

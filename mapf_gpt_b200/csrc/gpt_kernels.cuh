@@ -434,6 +434,176 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
     if (warp == 8) tmem_dealloc<256>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------
+// attn_persistent_kernel (head size 32): persistent CTAs (2 per SM) looping over (sequence, head) items with
+// double-buffered Q/K/V in smem -- the loads of the NEXT item are in flight during the softmax of the current one -- and
+// the probabilities kept in TENSOR MEMORY: each thread converts its row of S in place to bf16 pairs (tcgen05.st) and the
+// P V UMMA reads its A operand from TMEM (no 64 KB P tile in smem, which is what makes the second buffer fit).
+// TMEM (256 columns): S = [0,256); P (bf16x2) = [0,64) for keys 0..127 and [128,192) for keys 128..255 (each half of the
+// thread pair converts inside its own column range); [O | rowsum] = [64,112).
+// warps 0-7: softmax + epilogue, warp 8: bulk-copy producer, warp 9: UMMA issuer.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs a, int n_items)
+{
+    constexpr int HS = 32;
+    constexpr int Q_BYTES = 256 * HS * 2, K_BYTES = 256 * HS * 2, V_BYTES = 256 * (HS + 16) * 2;
+    constexpr int BUF_BYTES = Q_BYTES + K_BYTES + V_BYTES;     // 57 344
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * BUF_BYTES);
+    uint64_t *full = bars, *empty = bars + 2, *bS = bars + 4, *bP = bars + 5, *bO = bars + 6, *bE = bars + 7;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    // [2][128] row-max exchange in bf16: both halves of a row read the same two rounded values, and softmax does not care
+    // which offset is subtracted -- fp32 here would put the CTA 80 bytes over the two-CTAs-per-SM shared-memory budget
+    __nv_bfloat16 *redm = reinterpret_cast<__nv_bfloat16 *>(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        mbar_init(bS, 1); mbar_init(bP, 256); mbar_init(bO, 1); mbar_init(bE, 256);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc<256>(tmem_slot);
+    if (threadIdx.x < 256) {   // ones blocks of both V buffers (d-chunks HS/8, HS/8+1): never overwritten by the loads
+        const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            uint4 *o = reinterpret_cast<uint4 *>(smem + b * BUF_BYTES + Q_BYTES + K_BYTES + K_BYTES);
+            o[threadIdx.x] = ones;
+            o[256 + threadIdx.x] = ones;
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const size_t blk = (size_t)(HS / 8) * 256 * 8;   // elements per (seq, which, head)
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+                const int b = k & 1;
+                const int head = item % a.n_head, seq = item / a.n_head;
+                mbar_wait(&empty[b], ((k >> 1) & 1) ^ 1);
+                uint8_t *buf = smem + b * BUF_BYTES;
+                mbar_expect_tx(&full[b], Q_BYTES + 2 * K_BYTES);
+                bulk_g2s(buf, a.qkv + (((size_t)seq * 3 + 0) * a.n_head + head) * blk, Q_BYTES, &full[b]);
+                bulk_g2s(buf + Q_BYTES, a.qkv + (((size_t)seq * 3 + 1) * a.n_head + head) * blk, K_BYTES, &full[b]);
+                bulk_g2s(buf + Q_BYTES + K_BYTES, a.qkv + (((size_t)seq * 3 + 2) * a.n_head + head) * blk, K_BYTES, &full[b]);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            constexpr uint32_t idescS = umma_idesc_bf16(128, 256, 0, 0);
+            constexpr uint32_t idescO = umma_idesc_bf16(128, HS + 16, 0, 1);
+            int k = 0, t = 0;   // item counter, tile counter
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+                const int b = k & 1;
+                const uint32_t qa = smem_u32(smem + b * BUF_BYTES), ka = qa + Q_BYTES, va = ka + K_BYTES;
+                mbar_wait(&full[b], (k >> 1) & 1);
+                for (int qt = 0; qt < 2; qt++, t++) {
+                    if (t > 0) mbar_wait(bE, (t - 1) & 1);      // previous tile's O drained: the S columns are free
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < HS / 16; ks++)
+                        umma_ss(tmem, umma_desc(qa + qt * 2048 + ks * 2 * 4096, 4096, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128),
+                                idescS, ks != 0 ? 1u : 0u);
+                    umma_commit(bS);
+                    mbar_wait(bP, t & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 16; ks++)
+                        umma_ts(tmem + 64, tmem + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8), umma_desc(va + ks * 2 * 128, 128, 4096), idescO,
+                                ks != 0 ? 1u : 0u);
+                    umma_commit(bO);
+                }
+                umma_commit(&empty[b]);   // all UMMAs reading this buffer have retired -> the producer may refill it
+            }
+        }
+    } else {
+        const int q = warp & 3, kh = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const f32x2 sc2 = pk2(a.scale_log2e, a.scale_log2e);
+        int t = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int head = item % a.n_head, seq = item / a.n_head;
+            for (int qt = 0; qt < 2; qt++, t++) {
+                mbar_wait(bS, t & 1);
+                tc_fence_after();
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + c0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                }
+                redm[kh * 128 + r] = __float2bfloat16(mx);
+                named_bar_sync(1, 256);
+                mx = fmaxf(__bfloat162float(redm[r]), __bfloat162float(redm[128 + r]));
+                const float moff = mx * a.scale_log2e;
+                const f32x2 mo2 = pk2(-moff, -moff);
+#pragma unroll 1
+                for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + c0, v);
+                    tmem_wait_ld();
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const f32x2 xs = fma2(pk2u(v[2 * j], v[2 * j + 1]), sc2, mo2);
+                        float e0, e1;
+                        if (j & 1) {
+                            exp2_poly2(xs, e0, e1);
+                        } else {
+                            upk2(xs, e0, e1);
+                            e0 = ex2_approx(e0);
+                            e1 = ex2_approx(e1);
+                        }
+                        w[j] = pack_bf16x2(e0, e1);
+                    }
+                    tmem_st16(trow + kh * 128 + (c0 - kh * 128) / 2, w);   // P in place, inside this thread's own S range
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bP);
+                named_bar_sync(1, 256);                  // redm may be rewritten only after everybody has read it
+
+                mbar_wait(bO, t & 1);
+                tc_fence_after();
+                uint32_t sv[8], v[16];
+                tmem_ld8(trow + 64 + HS, sv);            // row sum
+                tmem_ld16(trow + 64 + kh * 16, v);       // 16 of the 32 output columns
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(bE);
+                const float inv = 1.0f / __uint_as_float(sv[0]);
+                const int mt = seq * 2 + qt;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+                    o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+                    o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+                    o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+                    const int col = head * HS + kh * 16 + 8 * j;
+                    uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
+                    *O = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<256>(tmem);
+}
+constexpr int attn_persistent_smem_bytes() { return 2 * (256 * 32 * 2 * 2 + 256 * 48 * 2) + 8 * 8 + 16 + 512; }
+static_assert(2 * (attn_persistent_smem_bytes() + 1024) <= 233472, "two persistent attention CTAs must fit one SM");
+
 template <int HS>
 constexpr int attn_smem_bytes() { return 128 * HS * 2 + 256 * HS * 2 + 256 * (HS + 16) * 2 + 128 * 256 * 2 + 7 * 8 + 16; }
 

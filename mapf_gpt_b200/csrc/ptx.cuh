@@ -179,6 +179,16 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (128 lanes x K/2 32-bit columns, two bf16 per column)
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // all previously issued UMMAs of this thread arrive on the mbarrier when complete
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
