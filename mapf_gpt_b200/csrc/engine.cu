@@ -92,6 +92,7 @@ struct mg_engine {
     float last_total_ms = 0.f, last_phase_ms[3] = {0.f, 0.f, 0.f};
     float kc_ms[KC_COUNT] = {0};
     long long *d_timeline = nullptr;   // test hook (mg_test_timeline)
+    int *d_attn_ctr = nullptr;         // work counter of the persistent attention kernel (self-resetting)
     CUtensorMap map_c2g{}, map_loc{};  // TMA descriptors of the FOV-window fields (observe_tma_kernel)
     std::vector<std::vector<uint8_t>> map_grids;   // large maps: host copies of the distinct grids (precompute tables per map)
     std::vector<uint16_t *> map_pre;               // device K x K tables
@@ -208,17 +209,17 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
     return MG_OK;
 }
 
-template <int C, int NT>
+template <int C, int NT, int UU = 0>
 static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT, int kc)
 {
-    using K = PostAttnCfg<C, NT>;
+    using K = PostAttnCfg<C, NT, UU>;
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
     prof_begin(e, kc);
-    post_attn_kernel<C, NT><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
+    post_attn_kernel<C, NT, UU><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
     prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
@@ -229,6 +230,8 @@ static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT, 
     // the HBM phases (tile load / store) and the compute phase of an SM do not overlap.  MAPF_GPT_B200_POST_NT=2 selects it.
     static const int nt_override = getenv("MAPF_GPT_B200_POST_NT") ? atoi(getenv("MAPF_GPT_B200_POST_NT")) : 0;
     const int kc = single_tiles ? KC_POST_LAST : KC_POST;
+    static const int u_override = getenv("MAPF_GPT_B200_POST_U") ? atoi(getenv("MAPF_GPT_B200_POST_U")) : 0;
+    if (C == 160 && u_override == 1) return launch_post_attn_c<160, 1, 1>(e, a, MT, kc);
     if (C == 160)
         return (nt_override == 2 && !single_tiles && MT % 2 == 0) ? launch_post_attn_c<160, 2>(e, a, MT, kc)
                                                                   : launch_post_attn_c<160, 1>(e, a, MT, kc);
@@ -303,8 +306,23 @@ static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cu
         attr_set = true;
     }
     const int n_items = n_seq * a.n_head;
+    AttnArgs aa = a;
+    if (e) {
+        if (!e->d_attn_ctr) {
+            CU(dalloc(&e->d_attn_ctr, 2));
+            CU(cudaMemsetAsync(e->d_attn_ctr, 0, 8, st));
+        }
+        aa.work_counter = e->d_attn_ctr;
+    } else {   // test hook without an engine: one synchronous caller at a time
+        static int *ctr = nullptr;
+        if (!ctr) {
+            CU(dalloc(&ctr, 2));
+            CU(cudaMemset(ctr, 0, 8));
+        }
+        aa.work_counter = ctr;
+    }
     if (e) prof_begin(e, KC_ATTN);
-    attn_persistent_kernel<<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(a, n_items);
+    attn_persistent_kernel<<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(aa, n_items);
     if (e) prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
@@ -744,6 +762,7 @@ void mg_engine_destroy(mg_engine *e)
     cudaDeviceSynchronize();
     EnvState &s = e->s;
     for (auto p : e->map_pre) cudaFree(p);
+    cudaFree(e->d_attn_ctr);
     cudaFree(s.bounds); cudaFree(s.map_of_env); cudaFree(s.cell_idx); cudaFree(s.pre); cudaFree(s.preK);
     cudaFree(s.obst); cudaFree(s.loc); cudaFree(s.c2g); cudaFree(s.pos); cudaFree(s.goal); cudaFree(s.hist);
     cudaFree(s.nextb); cudaFree(s.act); cudaFree(s.nag); cudaFree(s.dirty); cudaFree(s.tokens); cudaFree(s.logits);
@@ -1243,12 +1262,12 @@ int mg_test_timeline(mg_engine *e, int enable, long long *out)
     if (!e) return fail(MG_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     if (enable && !e->d_timeline) {
-        CU(dalloc(&e->d_timeline, 4 * 128));
-        CU(cudaMemset(e->d_timeline, 0, 4 * 128 * 8));
+        CU(dalloc(&e->d_timeline, 16 * 128));
+        CU(cudaMemset(e->d_timeline, 0, 16 * 128 * 8));
     }
     if (out && e->d_timeline) {
         CU(cudaStreamSynchronize(e->stream));
-        CU(cudaMemcpy(out, e->d_timeline, 4 * 128 * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out, e->d_timeline, 16 * 128 * 8, cudaMemcpyDeviceToHost));
     }
     if (!enable && e->d_timeline) { cudaFree(e->d_timeline); e->d_timeline = nullptr; }
     return MG_OK;

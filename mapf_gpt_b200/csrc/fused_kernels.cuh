@@ -69,7 +69,7 @@ __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean,
 //   * x is pre-loaded into the TMEM accumulator by the workers while the att tile is still in flight, so the c_proj
 //     UMMAs produce x1 = x + proj directly and the first epilogue has no global loads;
 //   * LayerNorm statistics are single-pass (sum, sum of squares) in packed fp32x2.
-template <int C, int NT>
+template <int C, int NT, int UU = 0>
 struct PostAttnCfg {
     static constexpr int HC = C / 2;                 // hidden chunk (FC N, proj2 K per chunk)
     static constexpr int NCH = 4 * C / HC;           // 8 chunks
@@ -77,12 +77,12 @@ struct PostAttnCfg {
     static constexpr int NPROJ = C / 16;             // units of the proj GEMM (one k-step each)
     static constexpr int NFC = C / 32;               // units per FC chunk (two k-steps each)
     static constexpr int NP2 = HC / 16;              // units per proj2 chunk (one k-step each)
-    static constexpr int U = C == 160 ? 5 : 4;       // units per stage
+    static constexpr int U = UU ? UU : (C == 160 ? 5 : 4);   // units per stage
     static constexpr int STAGE_BYTES = U * UNIT_BYTES;
     static constexpr int TOTAL_STAGES = (NPROJ + NCH * (NFC + NP2)) / U;
     static constexpr int A_BYTES = C * 256;          // [C/8][128][16B] per tile
     static constexpr int H_BYTES = HC * 256;         // [HC/8][128][16B] per tile
-    static constexpr int STAGES = NT == 2 ? 4 : (C <= 160 ? 2 : 3);
+    static constexpr int STAGES = UU ? (NT == 2 ? 4 : (C <= 160 ? 2 : 3)) * (C == 160 ? 5 : 4) / UU : (NT == 2 ? 4 : (C <= 160 ? 2 : 3));
     static constexpr int CTAS_PER_SM = (NT == 1 && C <= 160) ? 2 : 1;
     static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
@@ -95,11 +95,11 @@ struct PostAttnCfg {
     static_assert(TMEM_COLS <= 512, "post_attn_kernel: TMEM budget");
 };
 
-template <int C, int NT>
-__global__ void __launch_bounds__(PostAttnCfg<C, NT>::THREADS, PostAttnCfg<C, NT>::CTAS_PER_SM)
+template <int C, int NT, int UU = 0>
+__global__ void __launch_bounds__(PostAttnCfg<C, NT, UU>::THREADS, PostAttnCfg<C, NT, UU>::CTAS_PER_SM)
 post_attn_kernel(const PostAttnArgs a)
 {
-    using K = PostAttnCfg<C, NT>;
+    using K = PostAttnCfg<C, NT, UU>;
     constexpr int HC = K::HC, S = K::STAGES, U = K::U;
     constexpr int PROD_WARP = 8 * NT, MMA_WARP = 8 * NT + 1;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -179,7 +179,10 @@ post_attn_kernel(const PostAttnArgs a)
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ UMMA issuer
-        if (lane == 0) {
+        // The whole warp runs the control flow (waits, stage cursor), so descriptors stay in uniform registers; one elected
+        // lane issues.  (With everything inside `if (lane == 0)` ptxas rebuilt each descriptor in vector registers and moved
+        // it over with R2UR: ~90 cycles of issue per UMMA, more than the UMMA itself takes.)
+        {
             constexpr uint32_t idescC = umma_idesc_bf16(128, C, 0, 0);
             constexpr uint32_t idescH = umma_idesc_bf16(128, HC, 0, 0);
             const uint32_t a_addr = smem_u32(As), h_addr = smem_u32(Hs), r_addr = smem_u32(ring);
@@ -191,25 +194,32 @@ post_attn_kernel(const PostAttnArgs a)
                 return r_addr + s * K::STAGE_BYTES;
             };
             // proj: acc_main (pre-loaded with x) += att @ Wproj^T
-            MG_STAMP(0);
+            if (elect_one()) MG_STAMP(0);
+            __syncwarp();
             for (int t = 0; t < NT; t++) {
                 mbar_wait(&bar_att[t], 0);
                 mbar_wait(&bar_x[t], 0);
             }
             tc_fence_after();
-            MG_STAMP(1);
+            if (elect_one()) MG_STAMP(1);
+            __syncwarp();
             for (int st = 0; st < K::NPROJ / U; st++, i++) {
                 const uint32_t b = stage_wait(i);
+                if (elect_one()) {
 #pragma unroll
-                for (int t = 0; t < NT; t++)
+                    for (int t = 0; t < NT; t++)
 #pragma unroll
-                    for (int u = 0; u < U; u++)
-                        umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
-                                umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
-                umma_commit(&empty[i % S]);
+                        for (int u = 0; u < U; u++)
+                            umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
+                                    umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
+                    umma_commit(&empty[i % S]);
+                    if (st == K::NPROJ / U - 1) {
+                        umma_commit(bar_proj);
+                        MG_STAMP(2);
+                    }
+                }
+                __syncwarp();
             }
-            umma_commit(bar_proj);
-            MG_STAMP(2);
             auto fc = [&](int j) {
                 for (int st = 0; st < K::NFC / U; st++, i++) {
                     const uint32_t b = stage_wait(i);
@@ -220,19 +230,24 @@ post_attn_kernel(const PostAttnArgs a)
                             else mbar_wait(&bar_a1e[t], (j - 1) & 1);
                             tc_fence_after();
                         }
+                        if (elect_one()) {
 #pragma unroll
-                        for (int u = 0; u < U; u++)
+                            for (int u = 0; u < U; u++)
 #pragma unroll
-                            for (int ks = 0; ks < 2; ks++)
-                                umma_ss(tmem + t * K::TILE_COLS + C,
-                                        umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
-                                        umma_desc(b + u * K::UNIT_BYTES + ks * 2 * (HC * 16), HC * 16, 128), idescH,
-                                        (st | u | ks) != 0);
-                        if (st == K::NFC / U - 1) umma_commit(&bar_a1f[t]);
+                                for (int ks = 0; ks < 2; ks++)
+                                    umma_ss(tmem + t * K::TILE_COLS + C,
+                                            umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
+                                            umma_desc(b + u * K::UNIT_BYTES + ks * 2 * (HC * 16), HC * 16, 128), idescH,
+                                            (st | u | ks) != 0);
+                            if (st == K::NFC / U - 1) umma_commit(&bar_a1f[t]);
+                            if (t == NT - 1) {
+                                umma_commit(&empty[i % S]);
+                                if (st == K::NFC / U - 1) MG_STAMP(10 + 2 * j);
+                            }
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(&empty[i % S]);
                 }
-                MG_STAMP(10 + 2 * j);
             };
             auto p2 = [&](int j) {
                 for (int st = 0; st < K::NP2 / U; st++, i++) {
@@ -243,23 +258,29 @@ post_attn_kernel(const PostAttnArgs a)
                             mbar_wait(&bar_hf[t], j & 1);
                             tc_fence_after();
                         }
+                        if (elect_one()) {
 #pragma unroll
-                        for (int u = 0; u < U; u++)
-                            umma_ss(tmem + t * K::TILE_COLS, umma_desc(h_addr + t * K::H_BYTES + (st * U + u) * 4096, 2048, 128),
-                                    umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
-                        if (st == K::NP2 / U - 1) umma_commit(&bar_he[t]);
+                            for (int u = 0; u < U; u++)
+                                umma_ss(tmem + t * K::TILE_COLS, umma_desc(h_addr + t * K::H_BYTES + (st * U + u) * 4096, 2048, 128),
+                                        umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
+                            if (st == K::NP2 / U - 1) umma_commit(&bar_he[t]);
+                            if (t == NT - 1) {
+                                umma_commit(&empty[i % S]);
+                                if (st == K::NP2 / U - 1) {
+                                    if (j == K::NCH - 1) umma_commit(bar_done);
+                                    MG_STAMP(11 + 2 * j);
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(&empty[i % S]);
                 }
-                MG_STAMP(11 + 2 * j);
             };
             fc(0);
             for (int j = 0; j < K::NCH; j++) {
                 if (j + 1 < K::NCH) fc(j + 1);
                 p2(j);
             }
-            umma_commit(bar_done);
-            MG_STAMP(40);
             if (fuse_qkv) {
                 // next block's c_attn: [q|k|v] = LN1_next(x') @ Wqkv^T, one C-wide n-tile at a time in the main accumulator
                 for (int t = 0; t < NT; t++) mbar_wait(&bar_qa[t], 0);
@@ -273,16 +294,20 @@ post_attn_kernel(const PostAttnArgs a)
                                 mbar_wait(&bar_qe[t], (t3 - 1) & 1);
                                 tc_fence_after();
                             }
+                            if (elect_one()) {
 #pragma unroll
-                            for (int u = 0; u < U; u++)
-                                umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
-                                        umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, (st | u) != 0);
-                            if (st == K::NPROJ / U - 1) umma_commit(&bar_qf[t]);
+                                for (int u = 0; u < U; u++)
+                                    umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
+                                            umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, (st | u) != 0);
+                                if (st == K::NPROJ / U - 1) umma_commit(&bar_qf[t]);
+                                if (t == NT - 1) umma_commit(&empty[i % S]);
+                            }
+                            __syncwarp();
                         }
-                        umma_commit(&empty[i % S]);
                     }
                 }
-                MG_STAMP(41);
+                if (elect_one()) MG_STAMP(41);
+                __syncwarp();
             }
         }
     } else {

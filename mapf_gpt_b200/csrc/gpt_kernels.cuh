@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues
             constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
             uint32_t lboA = 2048, sboA = 128, lboB = BN * 16, sboB = 128;
             if (a.dbg_swap_lbo_sbo) {
@@ -122,15 +122,18 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t sb = sa + A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < BK / 16; ks++) {
-                    const uint64_t ad = umma_desc(sa + ks * 2 * 2048, lboA, sboA);
-                    const uint64_t bd = umma_desc(sb + ks * 2 * (BN * 16), lboB, sboB);
-                    umma_ss(tmem, ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < BK / 16; ks++) {
+                        const uint64_t ad = umma_desc(sa + ks * 2 * 2048, lboA, sboA);
+                        const uint64_t bd = umma_desc(sb + ks * 2 * (BN * 16), lboB, sboB);
+                        umma_ss(tmem, ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+                    if (kb == KB - 1) umma_commit(acc_bar);
                 }
-                umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+                __syncwarp();
             }
-            umma_commit(acc_bar);
         }
     } else {
         // ---- epilogue: thread == row
@@ -206,6 +209,8 @@ struct AttnArgs {
     int n_head, C;
     float scale_log2e;         // (1/sqrt(hs)) * log2(e)
     int dbg_variant;
+    int *work_counter;         // persistent kernel: [0] next unclaimed (sequence, head) item beyond the first gridDim.x,
+                               // [1] CTAs finished; both zero between launches (the last CTA resets them)
     long long *timeline;       // test hook: clock64() stamps of CTA 0..3 ([cta][128], ids 100..); nullptr in production
 };
 #define MG_ASTAMP(id)                                                                    \
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * BUF_BYTES);
     uint64_t *full = bars, *empty = bars + 2, *bS = bars + 4, *bP = bars + 5, *bO = bars + 6, *bE = bars + 7;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    volatile int *item_of = reinterpret_cast<volatile int *>(tmem_slot + 1);   // [2] item held by each buffer, -1 = no more work
     // [2][128] row-max exchange in bf16: both halves of a row read the same two rounded values, and softmax does not care
     // which offset is subtracted -- fp32 here would put the CTA 80 bytes over the two-CTAs-per-SM shared-memory budget
     __nv_bfloat16 *redm = reinterpret_cast<__nv_bfloat16 *>(tmem_slot + 4);
@@ -478,48 +484,77 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x == 0) MG_ASTAMP(126);
+    if (threadIdx.x == 0 && a.timeline != nullptr && blockIdx.x < 512) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.timeline[512 + blockIdx.x] = gt;
+    }
     const size_t blk = (size_t)(HS / 8) * 256 * 8;   // elements per (seq, which, head)
 
     if (warp == 8) {
         if (lane == 0) {
-            int k = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+            // items are claimed dynamically: the hardware favours the older of two co-resident CTAs, and with a static split
+            // the younger one finished 18 % later, alone on its SM
+            int item = blockIdx.x;
+            for (int k = 0;; k++) {
                 const int b = k & 1;
-                const int head = item % a.n_head, seq = item / a.n_head;
                 mbar_wait(&empty[b], ((k >> 1) & 1) ^ 1);
+                if (item >= n_items) {
+                    item_of[b] = -1;
+                    mbar_arrive(&full[b]);
+                    break;
+                }
+                item_of[b] = item;
+                const int head = item % a.n_head, seq = item / a.n_head;
                 uint8_t *buf = smem + b * BUF_BYTES;
                 mbar_expect_tx(&full[b], Q_BYTES + 2 * K_BYTES);
                 bulk_g2s(buf, a.qkv + (((size_t)seq * 3 + 0) * a.n_head + head) * blk, Q_BYTES, &full[b]);
                 bulk_g2s(buf + Q_BYTES, a.qkv + (((size_t)seq * 3 + 1) * a.n_head + head) * blk, K_BYTES, &full[b]);
                 bulk_g2s(buf + Q_BYTES + K_BYTES, a.qkv + (((size_t)seq * 3 + 2) * a.n_head + head) * blk, K_BYTES, &full[b]);
+                item = (int)gridDim.x + atomicAdd(a.work_counter, 1);
             }
         }
     } else if (warp == 9) {
-        if (lane == 0) {
-            constexpr uint32_t idescS = umma_idesc_bf16(128, 256, 0, 0);
-            constexpr uint32_t idescO = umma_idesc_bf16(128, HS + 16, 0, 1);
-            int k = 0, t = 0;   // item counter, tile counter
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
-                const int b = k & 1;
-                const uint32_t qa = smem_u32(smem + b * BUF_BYTES), ka = qa + Q_BYTES, va = ka + K_BYTES;
-                mbar_wait(&full[b], (k >> 1) & 1);
-                for (int qt = 0; qt < 2; qt++, t++) {
-                    if (t > 0) mbar_wait(bE, (t - 1) & 1);      // previous tile's O drained: the S columns are free
-                    tc_fence_after();
+        // the whole warp runs the loop (warp-uniform descriptors); one elected lane issues
+        constexpr uint32_t idescS = umma_idesc_bf16(128, 256, 0, 0);
+        constexpr uint32_t idescO = umma_idesc_bf16(128, HS + 16, 0, 1);
+        int t = 0;   // tile counter
+        for (int k = 0;; k++) {
+            const int b = k & 1;
+            const uint32_t qa = smem_u32(smem + b * BUF_BYTES), ka = qa + Q_BYTES, va = ka + K_BYTES;
+            mbar_wait(&full[b], (k >> 1) & 1);
+            if (item_of[b] < 0) {                           // no more work: release the workers with an empty commit
+                if (t > 0) mbar_wait(bE, (t - 1) & 1);
+                if (elect_one()) umma_commit(bS);
+                __syncwarp();
+                break;
+            }
+            for (int qt = 0; qt < 2; qt++, t++) {
+                if (t > 0) mbar_wait(bE, (t - 1) & 1);      // previous tile's O drained: the S columns are free
+                tc_fence_after();
+                if (elect_one()) {
+                    if (k == 40) MG_ASTAMP(100 + 3 * qt);
 #pragma unroll
                     for (int ks = 0; ks < HS / 16; ks++)
                         umma_ss(tmem, umma_desc(qa + qt * 2048 + ks * 2 * 4096, 4096, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128),
                                 idescS, ks != 0 ? 1u : 0u);
                     umma_commit(bS);
-                    mbar_wait(bP, t & 1);
-                    tc_fence_after();
+                }
+                __syncwarp();
+                mbar_wait(bP, t & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    if (k == 40) MG_ASTAMP(101 + 3 * qt);
 #pragma unroll
                     for (int ks = 0; ks < 16; ks++)
                         umma_ts(tmem + 64, tmem + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8), umma_desc(va + ks * 2 * 128, 128, 4096), idescO,
                                 ks != 0 ? 1u : 0u);
                     umma_commit(bO);
+                    if (k == 40) MG_ASTAMP(102 + 3 * qt);
+                    if (qt == 1) umma_commit(&empty[b]);   // all UMMAs reading this buffer have retired -> the producer may refill it
                 }
-                umma_commit(&empty[b]);   // all UMMAs reading this buffer have retired -> the producer may refill it
+                __syncwarp();
             }
         }
     } else {
@@ -527,12 +562,19 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
         const int r = q * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         const f32x2 sc2 = pk2(a.scale_log2e, a.scale_log2e);
-        int t = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int head = item % a.n_head, seq = item / a.n_head;
+        int t = 0, head = 0, seq = 0;
+        for (;;) {
             for (int qt = 0; qt < 2; qt++, t++) {
+                const bool stamp = threadIdx.x == 0 && (t >> 1) == 40;
                 mbar_wait(bS, t & 1);
+                if (qt == 0) {
+                    const int item = item_of[(t >> 1) & 1];
+                    if (item < 0) goto done;
+                    head = item % a.n_head;
+                    seq = item / a.n_head;
+                }
                 tc_fence_after();
+                if (stamp) MG_ASTAMP(110 + 8 * qt);
                 float mx = -INFINITY;
 #pragma unroll 1
                 for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
@@ -542,8 +584,10 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
                 }
+                if (stamp) MG_ASTAMP(111 + 8 * qt);
                 redm[kh * 128 + r] = __float2bfloat16(mx);
                 named_bar_sync(1, 256);
+                if (stamp) MG_ASTAMP(112 + 8 * qt);
                 mx = fmaxf(__bfloat162float(redm[r]), __bfloat162float(redm[128 + r]));
                 const float moff = mx * a.scale_log2e;
                 const f32x2 mo2 = pk2(-moff, -moff);
@@ -571,10 +615,12 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bP);
+                if (stamp) MG_ASTAMP(113 + 8 * qt);
                 named_bar_sync(1, 256);                  // redm may be rewritten only after everybody has read it
 
                 mbar_wait(bO, t & 1);
                 tc_fence_after();
+                if (stamp) MG_ASTAMP(114 + 8 * qt);
                 uint32_t sv[8], v[16];
                 tmem_ld8(trow + 64 + HS, sv);            // row sum
                 tmem_ld16(trow + 64 + kh * 16, v);       // 16 of the 32 output columns
@@ -594,11 +640,29 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                     uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
                     *O = o;
                 }
+                if (stamp) MG_ASTAMP(115 + 8 * qt);
             }
         }
     }
+done:
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) {   // the last CTA to leave re-arms the work counter for the next launch
+        __threadfence();
+        if (atomicAdd(a.work_counter + 1, 1) == (int)gridDim.x - 1) {
+            a.work_counter[0] = 0;
+            a.work_counter[1] = 0;
+        }
+    }
+    if (threadIdx.x == 0) MG_ASTAMP(127);
+    if (threadIdx.x == 0 && a.timeline != nullptr && blockIdx.x < 512) {   // per-CTA end time + SM id: load-balance picture
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.timeline[1024 + blockIdx.x] = smid;
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.timeline[1536 + blockIdx.x] = gt;
+    }
     if (warp == 9) tmem_dealloc<256>(tmem);
 }
 constexpr int attn_persistent_smem_bytes() { return 2 * (256 * 32 * 2 * 2 + 256 * 48 * 2) + 8 * 8 + 16 + 512; }

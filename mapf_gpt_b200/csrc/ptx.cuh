@@ -40,15 +40,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// suspend-time hint: a waiting warp sleeps in hardware instead of re-issuing try_wait/branch/yield (spinning cost a quarter
+// of all issued instructions of the attention kernel before this hint)
+#ifndef MG_MBAR_SUSPEND_HINT
+#define MG_MBAR_SUSPEND_HINT 0x989680u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MG_MBAR_SUSPEND_HINT)
         : "memory");
     return ok != 0;
 }

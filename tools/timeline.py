@@ -10,13 +10,26 @@ toks = np.random.default_rng(0).integers(0, 67, (8192, 256)).astype(np.int8)
 L = _lib.lib()
 eng.forward_tokens(toks)                      # warm
 L.mg_test_timeline(eng._h, 1, None)
+eng.set_profiling(True)
 eng.forward_tokens(toks)
-out = np.zeros((4, 128), np.int64)
+eng.synchronize()
+print("kernel times of this single forward (cold clocks, no sustained power cap):",
+      {k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in eng.kernel_times().items() if v["launches"]})
+eng.set_profiling(False)
+out = np.zeros((16, 128), np.int64)
 L.mg_test_timeline(eng._h, 0, out.ctypes.data_as(C.c_void_p))
 names = {0: "mma:start", 1: "mma:att ready", 2: "mma:proj issued", 3: "mma:ln2 ready", 40: "mma:all issued",
          50: "wrk:proj done", 51: "wrk:epi1 pass1", 52: "wrk:ln2 arrive", 90: "wrk:done seen", 91: "wrk:end"}
 names.update({100: "att:start", 101: "att:QK landed", 102: "att:P+V ready", 103: "att:PV issued", 110: "att:S seen",
               111: "att:max done", 112: "att:P arrive", 113: "att:O seen", 114: "att:end"})
+if "--classic-attn" not in sys.argv:   # persistent attention kernel: item 40 of the CTA, both query tiles
+    for k in range(100, 128):
+        names.pop(k, None)
+    for qt in range(2):
+        names.update({100 + 3 * qt: f"att{qt}:mma S issue", 101 + 3 * qt: f"att{qt}:mma P ready", 102 + 3 * qt: f"att{qt}:mma PV issued",
+                      110 + 8 * qt: f"att{qt}:wrk S seen", 111 + 8 * qt: f"att{qt}:wrk max done", 112 + 8 * qt: f"att{qt}:wrk max exchanged",
+                      113 + 8 * qt: f"att{qt}:wrk P arrive", 114 + 8 * qt: f"att{qt}:wrk O seen", 115 + 8 * qt: f"att{qt}:wrk end"})
+names.update({126: "att:CTA start", 127: "att:CTA end"})
 for j in range(8):
     names[10 + 2 * j] = f"mma:FC({j}) issued"; names[11 + 2 * j] = f"mma:P2({j}) issued"
     names[60 + 3 * j] = f"wrk:a1f({j}) seen"; names[61 + 3 * j] = f"wrk:a1e({j}) arrive"; names[62 + 3 * j] = f"wrk:hf({j}) arrive"
@@ -40,3 +53,18 @@ for cta in range(2):
     for t, n in ev:
         print(f"{t - t0:8d}  (+{t - prev:6d})  {n}")
         prev = t
+
+flat = out.reshape(-1)
+gt = flat[1536:1536 + 296]
+if gt.any():
+    sm = flat[1024:1024 + 296]
+    g = gt - gt.min()
+    print("persistent attention CTA end times (globaltimer ns after the first to finish): min %d median %d max %d" %
+          (g.min(), np.median(g), g.max()))
+    order = np.argsort(g)
+    print("slowest CTAs (cta, sm, ns):", [(int(c), int(sm[c]), int(g[c])) for c in order[-8:]])
+    print("fastest CTAs (cta, sm, ns):", [(int(c), int(sm[c]), int(g[c])) for c in order[:8]])
+    st = flat[512:512 + 296] - gt.min()
+    print("start times relative to first end: first-wave CTAs (0..147) median %d, second CTA per SM (148..295) median %d; durations median %d / %d" %
+          (np.median(st[:148]), np.median(st[148:]), np.median((g - st)[:148]), np.median((g - st)[148:])))
+    print("histogram of end times (10 bins):", np.histogram(g, 10)[0].tolist())
