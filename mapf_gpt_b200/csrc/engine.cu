@@ -172,7 +172,7 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
 {
     const int HC = C / 2, NCH = 8, NPROJ = C / 16, NFC = C / 32, NP2 = HC / 16;
     const size_t stage_elems = (size_t)16 * C;   // 32*C bytes
-    const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2) + (Wqkv_next ? 3 * NPROJ : 0)) * stage_elems;
+    const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2) + (Wqkv_next ? 6 * NFC : 0)) * stage_elems;
     std::vector<uint16_t> h(total, 0);
     size_t st = 0;
     auto put_kn = [&](size_t base, int kc, int rows, int n, int k8, float v) {   // [kc][rows][8]
@@ -198,12 +198,12 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
         if (j + 1 < NCH) put_fc(j + 1);
         put_p2(j);
     }
-    if (Wqkv_next)   // next block's c_attn [3C][C]: per n-tile of C rows, one k-step per unit (same unit format as proj)
-        for (int t3 = 0; t3 < 3; t3++)
-            for (int ks = 0; ks < NPROJ; ks++, st++)
-                for (int n = 0; n < C; n++)
-                    for (int k = 0; k < 16; k++)
-                        put_kn(st * stage_elems, k / 8, C, n, k % 8, Wqkv_next[(size_t)(t3 * C + n) * C + ks * 16 + k]);
+    if (Wqkv_next)   // next block's c_attn [3C][C]: six half n-tiles of HC rows in the FC-chunk stage format
+        for (int hh = 0; hh < 6; hh++)
+            for (int kb = 0; kb < NFC; kb++, st++)
+                for (int n = 0; n < HC; n++)
+                    for (int k = 0; k < 32; k++)
+                        put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wqkv_next[(size_t)(hh * HC + n) * C + kb * 32 + k]);
     CU(dalloc(out, total));
     CU(cudaMemcpy(*out, h.data(), total * 2, cudaMemcpyHostToDevice));
     return MG_OK;

@@ -35,9 +35,11 @@ struct PostAttnArgs {
     __nv_bfloat16 *qkv_out;        // [seq][3][head][hs/8][256][8]
     int n_head, hs;
 };
+// steady-state CTAs (not the first wave, whose loads all hit DRAM at once); single-tile launches have fewer CTAs and stamp nothing
+#define MG_STAMP_CTA0 2048u
 #define MG_STAMP(id)                                                                     \
     do {                                                                                 \
-        if (a.timeline != nullptr && blockIdx.x < 4) a.timeline[blockIdx.x * 128 + (id)] = clock64(); \
+        if (a.timeline != nullptr && (blockIdx.x - MG_STAMP_CTA0) < 4u) a.timeline[(blockIdx.x - MG_STAMP_CTA0) * 128 + (id)] = clock64(); \
     } while (0)
 
 // (v - mean) * rstd * gain for 8 consecutive columns -> 8 bf16 (one 16-byte store); a = rstd, b = -mean * rstd
@@ -87,8 +89,8 @@ struct PostAttnCfg {
     static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
     static constexpr int THREADS = 64 + 256 * NT;
-    static constexpr int QKV_STAGES = 3 * NPROJ / U;   // next block's c_attn: 3 n-tiles of C columns
-    static constexpr int NBAR = 2 * STAGES + 2 + NT * 10;
+    static constexpr int QKV_STAGES = 6 * NFC / U;     // next block's c_attn: 6 half n-tiles of HC columns (FC-chunk stage format)
+    static constexpr int NBAR = 2 * STAGES + 2 + NT * 14;
     static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * STAGE_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
     static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
@@ -119,9 +121,9 @@ post_attn_kernel(const PostAttnArgs a)
     uint64_t *bar_hf = bar_a1e + NT;     // [NT] hidden chunk written to smem (256 arrivals)
     uint64_t *bar_he = bar_hf + NT;      // [NT] hidden chunk consumed by the proj2 UMMAs
     uint64_t *bar_qa = bar_he + NT;      // [NT] fused QKV: LN1_next(x') in smem, accumulator free (256 arrivals)
-    uint64_t *bar_qf = bar_qa + NT;      // [NT] fused QKV: n-tile accumulated
-    uint64_t *bar_qe = bar_qf + NT;      // [NT] fused QKV: n-tile drained (256 arrivals)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_qe + NT);
+    uint64_t *bar_qf = bar_qa + NT;      // [NT][3] fused QKV: half n-tile accumulated in buffer b
+    uint64_t *bar_qe = bar_qf + 3 * NT;  // [NT][3] fused QKV: buffer b drained to registers (256 arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_qe + 3 * NT);
     uint32_t *qkv_off = tmem_slot + 2;   // uint4 offset of each 8-column group inside a sequence's q/k/v block
     const bool fuse_qkv = a.qkv_out != nullptr;
 
@@ -144,8 +146,10 @@ post_attn_kernel(const PostAttnArgs a)
             mbar_init(&bar_hf[t], 256);
             mbar_init(&bar_he[t], 1);
             mbar_init(&bar_qa[t], 256);
-            mbar_init(&bar_qf[t], 1);
-            mbar_init(&bar_qe[t], 256);
+            for (int b = 0; b < 3; b++) {
+                mbar_init(&bar_qf[t * 3 + b], 1);
+                mbar_init(&bar_qe[t * 3 + b], 256);
+            }
         }
         fence_barrier_init();
     }
@@ -282,24 +286,32 @@ post_attn_kernel(const PostAttnArgs a)
                 p2(j);
             }
             if (fuse_qkv) {
-                // next block's c_attn: [q|k|v] = LN1_next(x') @ Wqkv^T, one C-wide n-tile at a time in the main accumulator
+                // next block's c_attn: [q|k|v] = LN1_next(x') @ Wqkv^T as six HC-wide half n-tiles rotating through three
+                // accumulator buffers (the FC accumulator and the two halves of the main one, all free by now), so the
+                // UMMAs of half-tile h+1 run while the workers drain half-tile h
                 for (int t = 0; t < NT; t++) mbar_wait(&bar_qa[t], 0);
                 tc_fence_after();
-                for (int t3 = 0; t3 < 3; t3++) {
-                    for (int st = 0; st < K::NPROJ / U; st++, i++) {
+                for (int hh = 0; hh < 6; hh++) {
+                    const int buf = hh % 3;
+                    const uint32_t col = buf == 0 ? C : (buf == 1 ? 0 : HC);
+                    for (int st = 0; st < K::NFC / U; st++, i++) {
                         const uint32_t b = stage_wait(i);
 #pragma unroll
                         for (int t = 0; t < NT; t++) {
-                            if (st == 0 && t3 > 0) {
-                                mbar_wait(&bar_qe[t], (t3 - 1) & 1);
+                            if (st == 0 && hh >= 3) {
+                                mbar_wait(&bar_qe[t * 3 + buf], 0);
                                 tc_fence_after();
                             }
                             if (elect_one()) {
 #pragma unroll
                                 for (int u = 0; u < U; u++)
-                                    umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
-                                            umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, (st | u) != 0);
-                                if (st == K::NPROJ / U - 1) umma_commit(&bar_qf[t]);
+#pragma unroll
+                                    for (int ks = 0; ks < 2; ks++)
+                                        umma_ss(tmem + t * K::TILE_COLS + col,
+                                                umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
+                                                umma_desc(b + u * K::UNIT_BYTES + ks * 2 * (HC * 16), HC * 16, 128), idescH,
+                                                (st | u | ks) != 0);
+                                if (st == K::NFC / U - 1) umma_commit(&bar_qf[t * 3 + buf]);
                                 if (t == NT - 1) umma_commit(&empty[i % S]);
                             }
                             __syncwarp();
@@ -446,6 +458,7 @@ post_attn_kernel(const PostAttnArgs a)
                     sq2 = fma2(e1, e1, sq2);
                 }
             }
+            if (threadIdx.x == 0) MG_STAMP(92);
             if (a.xn_out != nullptr || fuse_qkv) {
                 {
                     float s0, s1, q0, q1;
@@ -479,29 +492,31 @@ post_attn_kernel(const PostAttnArgs a)
             tc_fence_before();
             fence_proxy_async_smem();
             mbar_arrive(&bar_qa[t]);
+            if (threadIdx.x == 0) MG_STAMP(93);
             const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
             uint4 *Oseq = reinterpret_cast<uint4 *>(a.qkv_out) + (size_t)seq * (3 * C / 8) * 256 + tok;
 #pragma unroll 1
-            for (int t3 = 0; t3 < 3; t3++) {
-                mbar_wait(&bar_qf[t], t3 & 1);
+            for (int hh = 0; hh < 6; hh++) {
+                const int buf = hh % 3;
+                const uint32_t col = (buf == 0 ? C : (buf == 1 ? 0 : HC)) + h * (HC / 2);
+                mbar_wait(&bar_qf[t * 3 + buf], (hh / 3) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(trow + c0, v);
-                    tmem_wait_ld();
+                if (threadIdx.x == 0) MG_STAMP(94 + hh);
+                uint32_t v[HC / 2];
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                        Oseq[qkv_off[(t3 * C + c0) / 8 + j]] = o;
-                    }
-                }
+                for (int c = 0; c < HC / 2; c += 8) tmem_ld8(trow + col + c, *reinterpret_cast<uint32_t(*)[8]>(&v[c]));
+                tmem_wait_ld();
                 tc_fence_before();
-                mbar_arrive(&bar_qe[t]);
+                mbar_arrive(&bar_qe[t * 3 + buf]);   // values are in registers: the issuer may reuse the buffer
+#pragma unroll
+                for (int j = 0; j < HC / 16; j++) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                    o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                    o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                    o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                    Oseq[qkv_off[(hh * HC + h * (HC / 2)) / 8 + j]] = o;
+                }
             }
         }
     }

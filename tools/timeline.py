@@ -29,6 +29,8 @@ if "--classic-attn" not in sys.argv:   # persistent attention kernel: item 40 of
         names.update({100 + 3 * qt: f"att{qt}:mma S issue", 101 + 3 * qt: f"att{qt}:mma P ready", 102 + 3 * qt: f"att{qt}:mma PV issued",
                       110 + 8 * qt: f"att{qt}:wrk S seen", 111 + 8 * qt: f"att{qt}:wrk max done", 112 + 8 * qt: f"att{qt}:wrk max exchanged",
                       113 + 8 * qt: f"att{qt}:wrk P arrive", 114 + 8 * qt: f"att{qt}:wrk O seen", 115 + 8 * qt: f"att{qt}:wrk end"})
+names.update({92: "wrk:x' stored", 93: "wrk:qa arrive (LN1_next in smem)"})
+names.update({94 + hh: f"wrk:qkv half-tile {hh} seen" for hh in range(6)})
 names.update({126: "att:CTA start", 127: "att:CTA end"})
 for j in range(8):
     names[10 + 2 * j] = f"mma:FC({j}) issued"; names[11 + 2 * j] = f"mma:P2({j}) issued"
