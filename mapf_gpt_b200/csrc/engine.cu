@@ -321,6 +321,19 @@ static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cu
         }
         aa.work_counter = ctr;
     }
+    static const bool narrow = getenv("MAPF_GPT_B200_ATTN_NARROW") != nullptr;   // two 8-warp CTAs per SM instead of one 16-warp CTA
+    if (!narrow) {
+        static bool wide_attr = false;
+        if (!wide_attr) {
+            CU(cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_wide_smem_bytes()));
+            wide_attr = true;
+        }
+        if (e) prof_begin(e, KC_ATTN);
+        attn_wide_kernel<<<std::min(n_items, n_sms), 576, attn_wide_smem_bytes(), st>>>(aa, n_items);
+        if (e) prof_end(e);
+        CU(cudaGetLastError());
+        return MG_OK;
+    }
     if (e) prof_begin(e, KC_ATTN);
     attn_persistent_kernel<<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(aa, n_items);
     if (e) prof_end(e);
@@ -405,6 +418,8 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
                 at.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
                 at.timeline = e->d_timeline;
+                static const int stamp_item = getenv("MAPF_GPT_B200_STAMP_ITEM") ? atoi(getenv("MAPF_GPT_B200_STAMP_ITEM")) : 40;
+                at.dbg_variant = stamp_item;   // which item of a persistent attention CTA tools/timeline.py stamps
                 if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
                 PostAttnArgs pa{};
                 pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;

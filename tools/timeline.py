@@ -29,6 +29,9 @@ if "--classic-attn" not in sys.argv:   # persistent attention kernel: item 40 of
         names.update({100 + 3 * qt: f"att{qt}:mma S issue", 101 + 3 * qt: f"att{qt}:mma P ready", 102 + 3 * qt: f"att{qt}:mma PV issued",
                       110 + 8 * qt: f"att{qt}:wrk S seen", 111 + 8 * qt: f"att{qt}:wrk max done", 112 + 8 * qt: f"att{qt}:wrk max exchanged",
                       113 + 8 * qt: f"att{qt}:wrk P arrive", 114 + 8 * qt: f"att{qt}:wrk O seen", 115 + 8 * qt: f"att{qt}:wrk end"})
+        if "--narrow-attn" not in sys.argv:   # attn_wide_kernel: ids 113-115 mean something else
+            names.update({113 + 8 * qt: f"att{qt}:wrk O(prev) drained", 114 + 8 * qt: f"att{qt}:wrk P arrive", 115 + 8 * qt: f"att{qt}:wrk O(prev) stored",
+                          101 + 3 * qt: f"att{qt}:mma P ready", 102 + 3 * qt: f"att{qt}:mma PV issued"})
 names.update({92: "wrk:x' stored", 93: "wrk:qa arrive (LN1_next in smem)"})
 names.update({94 + hh: f"wrk:qkv half-tile {hh} seen" for hh in range(6)})
 names.update({126: "att:CTA start", 127: "att:CTA end"})
@@ -57,16 +60,13 @@ for cta in range(2):
         prev = t
 
 flat = out.reshape(-1)
-gt = flat[1536:1536 + 296]
-if gt.any():
-    sm = flat[1024:1024 + 296]
+n_cta = int((flat[1536:2048] != 0).sum())
+gt = flat[1536:1536 + n_cta]
+if n_cta:
+    aux = flat[1024:1024 + n_cta]     # narrow kernel: SM id; wide kernel: items processed by the CTA
     g = gt - gt.min()
-    print("persistent attention CTA end times (globaltimer ns after the first to finish): min %d median %d max %d" %
-          (g.min(), np.median(g), g.max()))
-    order = np.argsort(g)
-    print("slowest CTAs (cta, sm, ns):", [(int(c), int(sm[c]), int(g[c])) for c in order[-8:]])
-    print("fastest CTAs (cta, sm, ns):", [(int(c), int(sm[c]), int(g[c])) for c in order[:8]])
-    st = flat[512:512 + 296] - gt.min()
-    print("start times relative to first end: first-wave CTAs (0..147) median %d, second CTA per SM (148..295) median %d; durations median %d / %d" %
-          (np.median(st[:148]), np.median(st[148:]), np.median((g - st)[:148]), np.median((g - st)[148:])))
-    print("histogram of end times (10 bins):", np.histogram(g, 10)[0].tolist())
+    st = flat[512:512 + n_cta] - gt.min()
+    print(f"persistent attention: {n_cta} CTAs; end times (ns after the first to finish): median {int(np.median(g))} max {int(g.max())}; "
+          f"durations ns: min {int((g - st).min())} median {int(np.median(g - st))} max {int((g - st).max())}")
+    print("per-CTA aux (items processed / SM id): min %d median %d max %d; CTA0 %d" % (aux.min(), np.median(aux), aux.max(), aux[0]))
+    print("histogram of aux:", np.histogram(aux, 8))
