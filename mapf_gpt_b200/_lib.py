@@ -5,11 +5,13 @@ The product path fails loudly when the CUDA library is missing: there is no CPU 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libmapf_gpt_b200.so"
+# MAPF_GPT_B200_LIB_PATH: developer switch for A/B runs of compile-time kernel variants (csrc/Makefile OUT= / EXTRA=)
+LIB_PATH = Path(os.environ.get("MAPF_GPT_B200_LIB_PATH") or _HERE / "libmapf_gpt_b200.so")
 _lib = None
 
 MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_STATE, MG_ERR_VOCAB = 0, -1, -2, -3, -4

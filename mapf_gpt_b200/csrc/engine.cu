@@ -45,6 +45,7 @@ struct Layer {
     float *ln1 = nullptr, *ln2 = nullptr;
     __nv_bfloat16 *wqkv = nullptr, *wproj = nullptr, *wfc = nullptr, *wproj2 = nullptr;
     __nv_bfloat16 *wstream = nullptr;   // fused post-attention kernel: stage images in consumption order
+    __nv_bfloat16 *wstream_pair = nullptr;   // the same stream for CTA pairs: every stage split into two N/2-row halves
 };
 struct Model {
     bool loaded = false;
@@ -167,16 +168,27 @@ static int upload_f32(const float *src, size_t n, float **out)
 
 // Stage stream of post_attn_kernel<C> (fused_kernels.cuh): proj k-steps, then FC(0), FC(1), P2(0), FC(2), ...
 // Wproj[C][C], Wfc[4C][C], Wproj2[C][4C] are torch Linear weights (row = output feature).
-static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, const float *Wqkv_next, int C,
-                                   __nv_bfloat16 **out)
+// split = 2 (CTA pairs, post_attn_kernel<.., CL = 2>): a stage of U units is stored as [half][unit][kc][rows/2][8], so that
+// CTA r of a pair copies one contiguous half-stage holding rows [r * rows/2, (r+1) * rows/2) of every unit.
+// LayerNorm gains are folded into the weights that consume the normalised activations (the kernel then writes plain
+// (x - mean) * rstd): ln_2's gain g2[k] scales column k of Wfc, the next block's ln_1 gain gn[k] scales column k of Wqkv_next.
+static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, const float *Wqkv_next,
+                                   const float *g2, const float *gn, int C, int split, __nv_bfloat16 **out)
 {
     const int HC = C / 2, NCH = 8, NPROJ = C / 16, NFC = C / 32, NP2 = HC / 16;
-    const size_t stage_elems = (size_t)16 * C;   // 32*C bytes
+    const int U = C == 160 ? 5 : 4;              // units per stage (PostAttnCfg::U)
+    const size_t stage_elems = (size_t)16 * C;   // 32*C bytes per unit
     const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2) + (Wqkv_next ? 6 * NFC : 0)) * stage_elems;
     std::vector<uint16_t> h(total, 0);
     size_t st = 0;
-    auto put_kn = [&](size_t base, int kc, int rows, int n, int k8, float v) {   // [kc][rows][8]
-        h[base + ((size_t)kc * rows + n) * 8 + k8] = f2bf(v);
+    auto put_kn = [&](size_t base, int kc, int rows, int n, int k8, float v) {   // [kc][rows][8]; base = unit index * stage_elems
+        if (split == 1) {
+            h[base + ((size_t)kc * rows + n) * 8 + k8] = f2bf(v);
+            return;
+        }
+        const size_t unit = base / stage_elems, rh = rows / 2;
+        const size_t half = n / rh, nn = n % rh;
+        h[(unit / U) * (U * stage_elems) + half * (U * stage_elems / 2) + (unit % U) * (stage_elems / 2) + ((size_t)kc * rh + nn) * 8 + k8] = f2bf(v);
     };
     for (int ks = 0; ks < NPROJ; ks++, st++)
         for (int n = 0; n < C; n++)
@@ -185,7 +197,7 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
         for (int kb = 0; kb < NFC; kb++, st++)
             for (int n = 0; n < HC; n++)
                 for (int k = 0; k < 32; k++)
-                    put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wfc[(size_t)(j * HC + n) * C + kb * 32 + k]);
+                    put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wfc[(size_t)(j * HC + n) * C + kb * 32 + k] * g2[kb * 32 + k]);
     };
     auto put_p2 = [&](int j) {
         for (int ks = 0; ks < NP2; ks++, st++)
@@ -203,23 +215,43 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
             for (int kb = 0; kb < NFC; kb++, st++)
                 for (int n = 0; n < HC; n++)
                     for (int k = 0; k < 32; k++)
-                        put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wqkv_next[(size_t)(hh * HC + n) * C + kb * 32 + k]);
+                        put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wqkv_next[(size_t)(hh * HC + n) * C + kb * 32 + k] * gn[kb * 32 + k]);
     CU(dalloc(out, total));
     CU(cudaMemcpy(*out, h.data(), total * 2, cudaMemcpyHostToDevice));
     return MG_OK;
 }
 
-template <int C, int NT, int UU = 0>
-static int launch_post_attn_c(mg_engine *e, const PostAttnArgs &a, int MT, int kc)
+#ifndef MG_POST_CL_DEFAULT
+#define MG_POST_CL_DEFAULT 1
+#endif
+template <int C, int NT, int UU = 0, int CL = 1>
+static int launch_post_attn_c(mg_engine *e, PostAttnArgs a, int MT, int kc)
 {
-    using K = PostAttnCfg<C, NT, UU>;
+    using K = PostAttnCfg<C, NT, UU, CL>;
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT, UU, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set = true;
     }
     prof_begin(e, kc);
-    post_attn_kernel<C, NT, UU><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
+    if (CL == 1) {
+        post_attn_kernel<C, NT, UU, CL><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
+    } else {
+        a.wstream = a.wstream_pair;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(MT / NT);
+        cfg.blockDim = dim3(K::THREADS);
+        cfg.dynamicSmemBytes = K::SMEM_BYTES;
+        cfg.stream = e->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, post_attn_kernel<C, NT, UU, CL>, a));
+    }
     prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
@@ -228,14 +260,18 @@ static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT, 
 {
     // NT = 1 (two CTAs per SM) measured faster than NT = 2 (one CTA per SM, shared weight stages): with one CTA per SM
     // the HBM phases (tile load / store) and the compute phase of an SM do not overlap.  MAPF_GPT_B200_POST_NT=2 selects it.
+    // MAPF_GPT_B200_POST_CL = 2: CTA pairs (cta_group::2 UMMAs, each SM streams half of the weights); needs an even tile count.
     static const int nt_override = getenv("MAPF_GPT_B200_POST_NT") ? atoi(getenv("MAPF_GPT_B200_POST_NT")) : 0;
+    static const int cl_req = getenv("MAPF_GPT_B200_POST_CL") ? atoi(getenv("MAPF_GPT_B200_POST_CL")) : MG_POST_CL_DEFAULT;
     const int kc = single_tiles ? KC_POST_LAST : KC_POST;
     static const int u_override = getenv("MAPF_GPT_B200_POST_U") ? atoi(getenv("MAPF_GPT_B200_POST_U")) : 0;
+    const bool pair = cl_req == 2 && MT % 2 == 0 && a.wstream_pair != nullptr;
     if (C == 160 && u_override == 1) return launch_post_attn_c<160, 1, 1>(e, a, MT, kc);
-    if (C == 160)
-        return (nt_override == 2 && !single_tiles && MT % 2 == 0) ? launch_post_attn_c<160, 2>(e, a, MT, kc)
-                                                                  : launch_post_attn_c<160, 1>(e, a, MT, kc);
-    if (C == 256) return launch_post_attn_c<256, 1>(e, a, MT, kc);
+    if (C == 160) {
+        if (nt_override == 2 && !single_tiles && MT % 2 == 0) return launch_post_attn_c<160, 2>(e, a, MT, kc);
+        return pair ? launch_post_attn_c<160, 1, 0, 2>(e, a, MT, kc) : launch_post_attn_c<160, 1>(e, a, MT, kc);
+    }
+    if (C == 256) return pair ? launch_post_attn_c<256, 1, 0, 2>(e, a, MT, kc) : launch_post_attn_c<256, 1>(e, a, MT, kc);
     return fail(MG_ERR_ARG, "post_attn: unsupported width %d", C);
 }
 
@@ -321,8 +357,8 @@ static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cu
         }
         aa.work_counter = ctr;
     }
-    static const bool narrow = getenv("MAPF_GPT_B200_ATTN_NARROW") != nullptr;   // two 8-warp CTAs per SM instead of one 16-warp CTA
-    if (!narrow) {
+    static const bool wide = getenv("MAPF_GPT_B200_ATTN_WIDE") != nullptr;   // experiment: one 16-warp CTA per SM (measured slower: 1.06 vs 1.01 ms)
+    if (wide) {
         static bool wide_attr = false;
         if (!wide_attr) {
             CU(cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_wide_smem_bytes()));
@@ -407,7 +443,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                         last_attn_kernel<64><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 1.0f / std::sqrt((float)hs));
                     prof_end(e);
                     PostAttnArgs pa{};
-                    pa.att = w.ATTc; pa.x = w.Xc; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;
+                    pa.att = w.ATTc; pa.x = w.Xc; pa.wstream = L.wstream; pa.wstream_pair = L.wstream_pair; pa.ln2_gain = L.ln2;
                     if ((rc = launch_post_attn(e, C, pa, (ns + 127) / 128, true))) return rc;
                     prof_begin(e, KC_HEAD);
                     head_compact_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.Xc, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
@@ -422,7 +458,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 at.dbg_variant = stamp_item;   // which item of a persistent attention CTA tools/timeline.py stamps
                 if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
                 PostAttnArgs pa{};
-                pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.ln2_gain = L.ln2;
+                pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.wstream_pair = L.wstream_pair; pa.ln2_gain = L.ln2;
                 pa.next_gain = last ? nullptr : m.layers[l + 1].ln1;
                 pa.xn_out = (last || m.fuse_qkv) ? nullptr : w.XN;
                 pa.qkv_out = (!last && m.fuse_qkv) ? w.QKV : nullptr;
@@ -786,7 +822,7 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(e->d_metrics);
     Model &m = e->model;
     cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti);
-    for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); }
+    for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); cudaFree(L.wstream_pair); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
     cudaFree(w.Xc); cudaFree(w.ATTc);
@@ -849,6 +885,7 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         const float *wproj = w;
         if ((rc = upload_packed(w, C, C, BN, &L.wproj))) return rc;
         w += CC;
+        const float *g2 = w;
         if ((rc = upload_f32(w, C, &L.ln2))) return rc;
         w += C;
         const float *wfc = w;
@@ -862,7 +899,9 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
             const bool has_next = (&L != &m.layers.back());
             const float *wqkv_next = has_next ? w + C : nullptr;     // skip ln_1[C] of the next block
             m.fuse_qkv = getenv("MAPF_GPT_B200_NO_QKV_FUSION") == nullptr;
-            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, C, &L.wstream))) return rc;
+            const float *gn = has_next ? w : nullptr;                 // ln_1 gain of the next block
+            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, g2, gn, C, 1, &L.wstream))) return rc;
+            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, g2, gn, C, 2, &L.wstream_pair))) return rc;
         }
     }
     if ((rc = upload_f32(w, C, &m.lnf))) return rc;

@@ -26,8 +26,9 @@ struct PostAttnArgs {
     const __nv_bfloat16 *att;      // A_ti [MT][C/8][128][8]
     float *x;                      // X_ti [MT][C/4][128][4], updated in place
     const __nv_bfloat16 *wstream;  // stage images for this layer
-    const float *ln2_gain;         // [C]
-    const float *next_gain;        // [C] ln_1 gain of the next block, or nullptr
+    const __nv_bfloat16 *wstream_pair;   // host side only: the CTA-pair format of the same stream (the launcher swaps it in)
+    const float *ln2_gain;         // [C] documentation only: ln_2's gain is folded into the c_fc rows of the stream
+    const float *next_gain;        // [C] ln_1 gain of the next block (xn_out path; folded into c_attn when qkv_out is set)
     __nv_bfloat16 *xn_out;         // A_ti for the next block's QKV GEMM, or nullptr
     long long *timeline;           // test hook: clock64() stamps of CTA 0..3 ([cta][128]); nullptr in production
     // fused QKV projection of the NEXT block (c_attn, model.py:50): xn never goes to HBM.  The 3 x 2 extra weight stages
@@ -52,6 +53,38 @@ __device__ __forceinline__ uint4 ln_pack8(const uint32_t *v, f32x2 a, f32x2 b, c
     o.w = pack_bf16x2_p(mul2(fma2(pk2u(v[6], v[7]), a, b), pk2(g1.z, g1.w)));
     return o;
 }
+// (v - mean) * rstd for 8 consecutive columns -> 8 bf16; the LayerNorm gain is folded into the weights that consume it
+__device__ __forceinline__ uint4 ln_pack8_ng(const uint32_t *v, f32x2 a, f32x2 b)
+{
+    uint4 o;
+    o.x = pack_bf16x2_p(fma2(pk2u(v[0], v[1]), a, b));
+    o.y = pack_bf16x2_p(fma2(pk2u(v[2], v[3]), a, b));
+    o.z = pack_bf16x2_p(fma2(pk2u(v[4], v[5]), a, b));
+    o.w = pack_bf16x2_p(fma2(pk2u(v[6], v[7]), a, b));
+    return o;
+}
+// N (multiple of 16) consecutive fp32 columns of this thread's TMEM lane; the caller waits once for the whole batch
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&v)[N])
+{
+    static_assert(N % 16 == 0, "tmem_ld_n: whole 16-column loads");
+#pragma unroll
+    for (int i = 0; i < N / 16; i++) tmem_ld16(taddr + 16 * i, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * i]));
+}
+template <int V> struct IntC { static constexpr int value = V; };
+// the thread's HALF columns in batches of <= 48: one TMEM round trip per batch instead of one per 16 columns
+#define MG_COL_BATCHES(HALF_, F)                                                 \
+    do {                                                                         \
+        static_assert((HALF_) == 80 || (HALF_) == 128, "column batches");        \
+        if constexpr ((HALF_) == 80) {                                           \
+            F(IntC<0>{}, IntC<48>{});                                            \
+            F(IntC<48>{}, IntC<32>{});                                           \
+        } else {                                                                 \
+            F(IntC<0>{}, IntC<48>{});                                            \
+            F(IntC<48>{}, IntC<48>{});                                           \
+            F(IntC<96>{}, IntC<32>{});                                           \
+        }                                                                        \
+    } while (0)
 // sum of squared deviations of 16 values, packed
 __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean, f32x2 acc)
 {
@@ -71,7 +104,7 @@ __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean,
 //   * x is pre-loaded into the TMEM accumulator by the workers while the att tile is still in flight, so the c_proj
 //     UMMAs produce x1 = x + proj directly and the first epilogue has no global loads;
 //   * LayerNorm statistics are single-pass (sum, sum of squares) in packed fp32x2.
-template <int C, int NT, int UU = 0>
+template <int C, int NT, int UU = 0, int CL = 1>
 struct PostAttnCfg {
     static constexpr int HC = C / 2;                 // hidden chunk (FC N, proj2 K per chunk)
     static constexpr int NCH = 4 * C / HC;           // 8 chunks
@@ -84,34 +117,52 @@ struct PostAttnCfg {
     static constexpr int TOTAL_STAGES = (NPROJ + NCH * (NFC + NP2)) / U;
     static constexpr int A_BYTES = C * 256;          // [C/8][128][16B] per tile
     static constexpr int H_BYTES = HC * 256;         // [HC/8][128][16B] per tile
-    static constexpr int STAGES = UU ? (NT == 2 ? 4 : (C <= 160 ? 2 : 3)) * (C == 160 ? 5 : 4) / UU : (NT == 2 ? 4 : (C <= 160 ? 2 : 3));
+    static constexpr int SLOT_BYTES = STAGE_BYTES / CL;   // CTA pair: each CTA holds its half (N/2 weight rows) of every stage
+    static constexpr int STAGES = CL * (UU ? (NT == 2 ? 4 : (C <= 160 ? 2 : 3)) * (C == 160 ? 5 : 4) / UU : (NT == 2 ? 4 : (C <= 160 ? 2 : 3)));
     static constexpr int CTAS_PER_SM = (NT == 1 && C <= 160) ? 2 : 1;
     static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
     static constexpr int THREADS = 64 + 256 * NT;
     static constexpr int QKV_STAGES = 6 * NFC / U;     // next block's c_attn: 6 half n-tiles of HC columns (FC-chunk stage format)
-    static constexpr int NBAR = 2 * STAGES + 2 + NT * 14;
-    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * STAGE_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
+    static constexpr int NBAR = 3 * STAGES + 2 + NT * 14;
+    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * SLOT_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
     static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
     static_assert(TMEM_COLS <= 512, "post_attn_kernel: TMEM budget");
+    static_assert(CL == 1 || (CL == 2 && NT == 1 && C % 32 == 0), "CTA pairs: one tile per CTA, N/2 a multiple of 16");
 };
 
-template <int C, int NT, int UU = 0>
-__global__ void __launch_bounds__(PostAttnCfg<C, NT, UU>::THREADS, PostAttnCfg<C, NT, UU>::CTAS_PER_SM)
+// CL = 2: CTA pair (cta_group::2).  The two CTAs of a cluster own adjacent 128-token tiles and run every GEMM as ONE M = 256
+// UMMA issued by the leader (rank 0): A = each CTA's own tile, B = N/2 weight rows from each CTA's ring, D = 128 rows in each
+// CTA's TMEM.  Each SM therefore pulls only HALF of the weight stream through L2 -> SM (the kernel was bound there:
+// 36 B/clk/SM of the 42 B/clk/SM the L2 slices deliver, profiles/r01c_launch_list_summary.md; multicasting full stages to
+// both CTAs was measured and does not help -- the SM-side ingest is what counts).  Cross-CTA protocol:
+//   * workers of both CTAs arrive (one elected lane per warp) on the LEADER's barriers; the leader's commits are multicast
+//     to the barriers of both CTAs;
+//   * the peer's otherwise idle UMMA warp relays "my half of stage i landed" (and "my att tile landed") to the leader.
+template <int C, int NT, int UU = 0, int CL = 1>
+__global__ void __launch_bounds__(PostAttnCfg<C, NT, UU, CL>::THREADS, PostAttnCfg<C, NT, UU, CL>::CTAS_PER_SM)
 post_attn_kernel(const PostAttnArgs a)
 {
-    using K = PostAttnCfg<C, NT, UU>;
+    using K = PostAttnCfg<C, NT, UU, CL>;
     constexpr int HC = K::HC, S = K::STAGES, U = K::U;
+    constexpr bool PAIR = CL == 2;
+    constexpr int WARR = 8 * CL;              // arrivals on a worker -> issuer barrier: one per worker warp of the CTA group
+    constexpr int CB = C / CL, HB = HC / CL;  // weight rows per CTA of a C-wide / HC-wide B operand
+    constexpr int UNIT_B = K::UNIT_BYTES / CL;
+    constexpr uint32_t UM = 128 * CL;         // UMMA M
     constexpr int PROD_WARP = 8 * NT, MMA_WARP = 8 * NT + 1;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *As = smem;                                   // [NT] A tiles
     uint8_t *Hs = As + NT * K::A_BYTES;                   // [NT] hidden-chunk buffers
     uint8_t *ring = Hs + NT * K::H_BYTES;
-    float *red = reinterpret_cast<float *>(ring + S * K::STAGE_BYTES);   // [NT][2 kinds][2 halves][128]
+    float *red = reinterpret_cast<float *>(ring + S * K::SLOT_BYTES);    // [NT][2 kinds][2 halves][128]
     uint64_t *full = reinterpret_cast<uint64_t *>(red + NT * 4 * 128);
     uint64_t *empty = full + S;
-    uint64_t *bar_proj = empty + S;      // proj UMMAs retired (all tiles)
+    uint64_t *pfull = empty + S;         // leader only: the peer's half of the stage landed (relayed)
+    uint64_t *bar_proj = pfull + S;      // proj UMMAs retired (all tiles)
     uint64_t *bar_done = bar_proj + 1;   // all UMMAs retired
     uint64_t *bar_att = bar_done + 1;    // [NT] A tile landed (tx)
     uint64_t *bar_x = bar_att + NT;      // [NT] x pre-loaded into the TMEM accumulator (256 arrivals)
@@ -130,25 +181,50 @@ post_attn_kernel(const PostAttnArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt0 = blockIdx.x * NT;
 
-    if (threadIdx.x == 0) {
+    const int n_stages = K::TOTAL_STAGES + (fuse_qkv ? K::QKV_STAGES : 0);
+    if (warp == PROD_WARP && lane == 0) {
+        // the producer owns the barriers of its copies and starts them before the CTA-wide (and cluster-wide) rendezvous:
+        // the att tile and the first S weight stages are in flight while TMEM is being allocated
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&pfull[s], 1);
         }
+        for (int t = 0; t < NT; t++) mbar_init(&bar_att[t], 1);
+        fence_barrier_init();
+        fence_proxy_async_smem();
+        for (int t = 0; t < NT; t++) {
+            mbar_expect_tx(&bar_att[t], K::A_BYTES);
+            bulk_g2s(As + t * K::A_BYTES, a.att + (size_t)(mt0 + t) * C * 128, K::A_BYTES, &bar_att[t]);
+        }
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.wstream);
+        for (int i = 0; i < S && i < n_stages; i++) {
+            mbar_expect_tx(&full[i], K::SLOT_BYTES);
+            bulk_g2s(ring + i * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[i]);
+        }
+    }
+    // workers: the residual tile is on its way to registers meanwhile (it goes into the TMEM accumulator after the rendezvous)
+    constexpr int HALF = C / 2;                           // residual columns handled by one worker thread
+    float4 xv[HALF / 4];
+    if (warp < 8 * NT) {
+        const float4 *Xl = reinterpret_cast<const float4 *>(a.x) + (size_t)(mt0 + (warp >> 3)) * (C / 4) * 128 + (warp & 3) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < HALF / 4; j++) xv[j] = Xl[(size_t)(((warp >> 2) & 1) * (HALF / 4) + j) * 128];
+    }
+    if (threadIdx.x == 0) {
         mbar_init(bar_proj, 1);
         mbar_init(bar_done, 1);
         for (int t = 0; t < NT; t++) {
-            mbar_init(&bar_att[t], 1);
-            mbar_init(&bar_x[t], 256);
-            mbar_init(&bar_ln2[t], 256);
+            mbar_init(&bar_x[t], WARR + (PAIR ? 1 : 0));   // + the peer's "att tile landed" relay
+            mbar_init(&bar_ln2[t], WARR);
             mbar_init(&bar_a1f[t], 1);
-            mbar_init(&bar_a1e[t], 256);
-            mbar_init(&bar_hf[t], 256);
+            mbar_init(&bar_a1e[t], WARR);
+            mbar_init(&bar_hf[t], WARR);
             mbar_init(&bar_he[t], 1);
-            mbar_init(&bar_qa[t], 256);
+            mbar_init(&bar_qa[t], WARR);
             for (int b = 0; b < 3; b++) {
                 mbar_init(&bar_qf[t * 3 + b], 1);
-                mbar_init(&bar_qe[t * 3 + b], 256);
+                mbar_init(&bar_qe[t * 3 + b], WARR);
             }
         }
         fence_barrier_init();
@@ -159,27 +235,55 @@ post_attn_kernel(const PostAttnArgs a)
         const int head = rem / a.hs, d0 = rem - head * a.hs;
         qkv_off[threadIdx.x] = (uint32_t)(((which * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256);
     }
-    if (warp == MMA_WARP) tmem_alloc<K::TMEM_COLS>(tmem_slot);
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_alloc_pair<K::TMEM_COLS>(tmem_slot);
+        else tmem_alloc<K::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();         // the barriers of both CTAs exist before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // issuer -> workers (and ring slot release): when the UMMAs issued so far have retired
+    auto commit = [&](uint64_t *bar) {
+        if (PAIR) umma_commit_pair(bar, (uint16_t)3);
+        else umma_commit(bar);
+    };
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if (PAIR) umma_ss_pair(d, ad, bd, idesc, acc);
+        else umma_ss(d, ad, bd, idesc, acc);
+    };
+    // workers -> issuer: every lane has fenced its own writes; one elected lane arrives on the (leader's) barrier
+    auto arrive_issuer = [&](uint64_t *bar) {
+        __syncwarp();
+        if (lane == 0) {
+            if (!PAIR || leader) mbar_arrive(bar);
+            else mbar_arrive_cluster(bar, 0);
+        }
+        __syncwarp();
+    };
 
     if (warp == PROD_WARP) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
-            for (int t = 0; t < NT; t++) {
-                mbar_expect_tx(&bar_att[t], K::A_BYTES);
-                bulk_g2s(As + t * K::A_BYTES, a.att + (size_t)(mt0 + t) * C * 128, K::A_BYTES, &bar_att[t]);
-            }
             const uint8_t *src = reinterpret_cast<const uint8_t *>(a.wstream);
-            const int n_stages = K::TOTAL_STAGES + (fuse_qkv ? K::QKV_STAGES : 0);
-            for (int i = 0; i < n_stages; i++) {
+            for (int i = S; i < n_stages; i++) {
                 const int s = i % S;
                 mbar_wait(&empty[s], ((i / S) & 1) ^ 1);
-                mbar_expect_tx(&full[s], K::STAGE_BYTES);
-                bulk_g2s(ring + s * K::STAGE_BYTES, src + (size_t)i * K::STAGE_BYTES, K::STAGE_BYTES, &full[s]);
+                mbar_expect_tx(&full[s], K::SLOT_BYTES);
+                bulk_g2s(ring + s * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[s]);
             }
+        }
+    } else if (warp == MMA_WARP && PAIR && !leader) {
+        // ------------------------------------------------------------------ peer of a CTA pair: relay "landed" to the leader
+        mbar_wait(&bar_att[0], 0);
+        if (lane == 0) mbar_arrive_cluster(&bar_x[0], 0);
+        __syncwarp();
+        for (int i = 0; i < n_stages; i++) {
+            const int s = i % S;
+            mbar_wait(&full[s], (i / S) & 1);
+            if (lane == 0) mbar_arrive_cluster(&pfull[s], 0);
+            __syncwarp();
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ UMMA issuer
@@ -187,15 +291,16 @@ post_attn_kernel(const PostAttnArgs a)
         // lane issues.  (With everything inside `if (lane == 0)` ptxas rebuilt each descriptor in vector registers and moved
         // it over with R2UR: ~90 cycles of issue per UMMA, more than the UMMA itself takes.)
         {
-            constexpr uint32_t idescC = umma_idesc_bf16(128, C, 0, 0);
-            constexpr uint32_t idescH = umma_idesc_bf16(128, HC, 0, 0);
+            constexpr uint32_t idescC = umma_idesc_bf16(UM, C, 0, 0);
+            constexpr uint32_t idescH = umma_idesc_bf16(UM, HC, 0, 0);
             const uint32_t a_addr = smem_u32(As), h_addr = smem_u32(Hs), r_addr = smem_u32(ring);
             int i = 0;  // stage cursor
             auto stage_wait = [&](int idx) -> uint32_t {
                 const int s = idx % S;
                 mbar_wait(&full[s], (idx / S) & 1);
+                if (PAIR) mbar_wait(&pfull[s], (idx / S) & 1);
                 tc_fence_after();
-                return r_addr + s * K::STAGE_BYTES;
+                return r_addr + s * K::SLOT_BYTES;
             };
             // proj: acc_main (pre-loaded with x) += att @ Wproj^T
             if (elect_one()) MG_STAMP(0);
@@ -214,11 +319,11 @@ post_attn_kernel(const PostAttnArgs a)
                     for (int t = 0; t < NT; t++)
 #pragma unroll
                         for (int u = 0; u < U; u++)
-                            umma_ss(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
-                                    umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
-                    umma_commit(&empty[i % S]);
+                            mma(tmem + t * K::TILE_COLS, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
+                                umma_desc(b + u * UNIT_B, CB * 16, 128), idescC, 1u);
+                    commit(&empty[i % S]);
                     if (st == K::NPROJ / U - 1) {
-                        umma_commit(bar_proj);
+                        commit(bar_proj);
                         MG_STAMP(2);
                     }
                 }
@@ -239,13 +344,13 @@ post_attn_kernel(const PostAttnArgs a)
                             for (int u = 0; u < U; u++)
 #pragma unroll
                                 for (int ks = 0; ks < 2; ks++)
-                                    umma_ss(tmem + t * K::TILE_COLS + C,
-                                            umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
-                                            umma_desc(b + u * K::UNIT_BYTES + ks * 2 * (HC * 16), HC * 16, 128), idescH,
-                                            (st | u | ks) != 0);
-                            if (st == K::NFC / U - 1) umma_commit(&bar_a1f[t]);
+                                    mma(tmem + t * K::TILE_COLS + C,
+                                        umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
+                                        umma_desc(b + u * UNIT_B + ks * 2 * (HB * 16), HB * 16, 128), idescH,
+                                        (st | u | ks) != 0);
+                            if (st == K::NFC / U - 1) commit(&bar_a1f[t]);
                             if (t == NT - 1) {
-                                umma_commit(&empty[i % S]);
+                                commit(&empty[i % S]);
                                 if (st == K::NFC / U - 1) MG_STAMP(10 + 2 * j);
                             }
                         }
@@ -265,13 +370,13 @@ post_attn_kernel(const PostAttnArgs a)
                         if (elect_one()) {
 #pragma unroll
                             for (int u = 0; u < U; u++)
-                                umma_ss(tmem + t * K::TILE_COLS, umma_desc(h_addr + t * K::H_BYTES + (st * U + u) * 4096, 2048, 128),
-                                        umma_desc(b + u * K::UNIT_BYTES, C * 16, 128), idescC, 1u);
-                            if (st == K::NP2 / U - 1) umma_commit(&bar_he[t]);
+                                mma(tmem + t * K::TILE_COLS, umma_desc(h_addr + t * K::H_BYTES + (st * U + u) * 4096, 2048, 128),
+                                    umma_desc(b + u * UNIT_B, CB * 16, 128), idescC, 1u);
+                            if (st == K::NP2 / U - 1) commit(&bar_he[t]);
                             if (t == NT - 1) {
-                                umma_commit(&empty[i % S]);
+                                commit(&empty[i % S]);
                                 if (st == K::NP2 / U - 1) {
-                                    if (j == K::NCH - 1) umma_commit(bar_done);
+                                    if (j == K::NCH - 1) commit(bar_done);
                                     MG_STAMP(11 + 2 * j);
                                 }
                             }
@@ -307,12 +412,12 @@ post_attn_kernel(const PostAttnArgs a)
                                 for (int u = 0; u < U; u++)
 #pragma unroll
                                     for (int ks = 0; ks < 2; ks++)
-                                        umma_ss(tmem + t * K::TILE_COLS + col,
-                                                umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
-                                                umma_desc(b + u * K::UNIT_BYTES + ks * 2 * (HC * 16), HC * 16, 128), idescH,
-                                                (st | u | ks) != 0);
-                                if (st == K::NFC / U - 1) umma_commit(&bar_qf[t * 3 + buf]);
-                                if (t == NT - 1) umma_commit(&empty[i % S]);
+                                        mma(tmem + t * K::TILE_COLS + col,
+                                            umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
+                                            umma_desc(b + u * UNIT_B + ks * 2 * (HB * 16), HB * 16, 128), idescH,
+                                            (st | u | ks) != 0);
+                                if (st == K::NFC / U - 1) commit(&bar_qf[t * 3 + buf]);
+                                if (t == NT - 1) commit(&empty[i % S]);
                             }
                             __syncwarp();
                         }
@@ -330,7 +435,6 @@ post_attn_kernel(const PostAttnArgs a)
         const int mt = mt0 + t;
         const uint32_t trow = tmem + t * K::TILE_COLS + ((uint32_t)(q * 32) << 16);
         uint8_t *At = As + t * K::A_BYTES;
-        constexpr int HALF = C / 2;                       // columns of the residual handled by this thread
         float *red_s = red + t * 512, *red_q = red_s + 256;
         const float inv_c = 1.0f / (float)C;
         const uint32_t nb = 1 + t;                        // named barrier of this tile's 256 workers
@@ -339,9 +443,6 @@ post_attn_kernel(const PostAttnArgs a)
         // ---- x -> TMEM accumulator (overlaps the att tile load); c_proj then accumulates onto it.
         // All loads are issued before the first TMEM store so the thread pays ONE memory round trip.
         {
-            float4 xv[HALF / 4];
-#pragma unroll
-            for (int j = 0; j < HALF / 4; j++) xv[j] = Xg[(size_t)(h * (HALF / 4) + j) * 128];
 #pragma unroll
             for (int i = 0; i < HALF / 16; i++) {
                 uint32_t v[16];
@@ -355,7 +456,7 @@ post_attn_kernel(const PostAttnArgs a)
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bar_x[t]);
+        arrive_issuer(&bar_x[t]);
 
         // ---- epilogue 1: LN2(x1) -> A tile (x1 = x + proj stays in TMEM)
         mbar_wait(bar_proj, 0);
@@ -363,18 +464,19 @@ post_attn_kernel(const PostAttnArgs a)
         if (threadIdx.x == 0) MG_STAMP(50);
         {
             f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
-#pragma unroll 1
-            for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + c0, v);
+            auto stats = [&](auto c0_, auto n_) {
+                constexpr int C0 = decltype(c0_)::value, N = decltype(n_)::value;
+                uint32_t v[N];
+                tmem_ld_n<N>(trow + h * HALF + C0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
+                for (int j = 0; j < N; j += 2) {
                     const f32x2 e = pk2u(v[j], v[j + 1]);
                     sum2 = add2(sum2, e);
                     sq2 = fma2(e, e, sq2);
                 }
-            }
+            };
+            MG_COL_BATCHES(HALF, stats);
             if (threadIdx.x == 0) MG_STAMP(51);
             {
                 float s0, s1, q0, q1;
@@ -388,20 +490,19 @@ post_attn_kernel(const PostAttnArgs a)
             const float var = fmaxf((red_q[r] + red_q[128 + r]) * inv_c - mean * mean, 0.f);
             const float rstd = rsqrtf(var + 1e-5f);
             const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
-            const float4 *g4 = reinterpret_cast<const float4 *>(a.ln2_gain);
-#pragma unroll 1
-            for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + c0, v);
+            auto norm = [&](auto c0_, auto n_) {
+                constexpr int C0 = decltype(c0_)::value, N = decltype(n_)::value;
+                uint32_t v[N];
+                tmem_ld_n<N>(trow + h * HALF + C0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 2; j++)
-                    *reinterpret_cast<uint4 *>(At + ((c0 / 8 + j) * 128 + r) * 16) =
-                        ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
-            }
+                for (int j = 0; j < N / 8; j++)
+                    *reinterpret_cast<uint4 *>(At + (((h * HALF + C0) / 8 + j) * 128 + r) * 16) = ln_pack8_ng(&v[8 * j], la, lb);
+            };
+            MG_COL_BATCHES(HALF, norm);
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(&bar_ln2[t]);
+            arrive_issuer(&bar_ln2[t]);
             if (threadIdx.x == 0) MG_STAMP(52);
         }
 
@@ -419,7 +520,7 @@ post_attn_kernel(const PostAttnArgs a)
             for (int g = 0; g < NV; g++) tmem_ld8(trow + C + h * HH + g * 8, v[g]);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(&bar_a1e[t]);
+            arrive_issuer(&bar_a1e[t]);
             if (threadIdx.x == 0) MG_STAMP(61 + 3 * j);
             uint4 o[NV];
 #pragma unroll
@@ -433,7 +534,7 @@ post_attn_kernel(const PostAttnArgs a)
 #pragma unroll
             for (int g = 0; g < NV; g++) *reinterpret_cast<uint4 *>(Hb + ((h * NV + g) * 128 + r) * 16) = o[g];
             fence_proxy_async_smem();
-            mbar_arrive(&bar_hf[t]);
+            arrive_issuer(&bar_hf[t]);
             if (threadIdx.x == 0) MG_STAMP(62 + 3 * j);
         }
 
@@ -443,21 +544,22 @@ post_attn_kernel(const PostAttnArgs a)
         if (threadIdx.x == 0) MG_STAMP(90);
         {
             f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
-#pragma unroll 1
-            for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + c0, v);
+            auto store_x = [&](auto c0_, auto n_) {
+                constexpr int C0 = decltype(c0_)::value, N = decltype(n_)::value;
+                uint32_t v[N];
+                tmem_ld_n<N>(trow + h * HALF + C0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    Xg[(size_t)(c0 / 4 + j) * 128] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
-                                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                for (int j = 0; j < N / 4; j++) {
+                    Xg[(size_t)((h * HALF + C0) / 4 + j) * 128] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
+                                                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     const f32x2 e0 = pk2u(v[4 * j + 0], v[4 * j + 1]), e1 = pk2u(v[4 * j + 2], v[4 * j + 3]);
                     sum2 = add2(sum2, add2(e0, e1));
                     sq2 = fma2(e0, e0, sq2);
                     sq2 = fma2(e1, e1, sq2);
                 }
-            }
+            };
+            MG_COL_BATCHES(HALF, store_x);
             if (threadIdx.x == 0) MG_STAMP(92);
             if (a.xn_out != nullptr || fuse_qkv) {
                 {
@@ -472,18 +574,29 @@ post_attn_kernel(const PostAttnArgs a)
                 const float var = fmaxf((red_q[r] + red_q[128 + r]) * inv_c - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + 1e-5f);
                 const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
-                const float4 *g4 = reinterpret_cast<const float4 *>(a.next_gain);
-                uint4 *O = reinterpret_cast<uint4 *>(a.xn_out) + (size_t)mt * (C / 8) * 128 + r;
-#pragma unroll 1
-                for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(trow + c0, v);
-                    tmem_wait_ld();
+                if (fuse_qkv) {
+                    auto norm = [&](auto c0_, auto n_) {
+                        constexpr int C0 = decltype(c0_)::value, N = decltype(n_)::value;
+                        uint32_t v[N];
+                        tmem_ld_n<N>(trow + h * HALF + C0, v);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const uint4 o = ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
-                        if (fuse_qkv) *reinterpret_cast<uint4 *>(At + ((c0 / 8 + j) * 128 + r) * 16) = o;
-                        else O[(size_t)(c0 / 8 + j) * 128] = o;
+                        for (int j = 0; j < N / 8; j++)
+                            *reinterpret_cast<uint4 *>(At + (((h * HALF + C0) / 8 + j) * 128 + r) * 16) = ln_pack8_ng(&v[8 * j], la, lb);
+                    };
+                    MG_COL_BATCHES(HALF, norm);
+                } else {
+                    const float4 *g4 = reinterpret_cast<const float4 *>(a.next_gain);
+                    uint4 *O = reinterpret_cast<uint4 *>(a.xn_out) + (size_t)mt * (C / 8) * 128 + r;
+#pragma unroll 1
+                    for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(trow + c0, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            O[(size_t)(c0 / 8 + j) * 128] =
+                                ln_pack8(&v[8 * j], la, lb, __ldg(g4 + c0 / 4 + 2 * j), __ldg(g4 + c0 / 4 + 2 * j + 1));
                     }
                 }
             }
@@ -491,7 +604,7 @@ post_attn_kernel(const PostAttnArgs a)
         if (fuse_qkv) {
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(&bar_qa[t]);
+            arrive_issuer(&bar_qa[t]);
             if (threadIdx.x == 0) MG_STAMP(93);
             const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
             uint4 *Oseq = reinterpret_cast<uint4 *>(a.qkv_out) + (size_t)seq * (3 * C / 8) * 256 + tok;
@@ -507,7 +620,7 @@ post_attn_kernel(const PostAttnArgs a)
                 for (int c = 0; c < HC / 2; c += 8) tmem_ld8(trow + col + c, *reinterpret_cast<uint32_t(*)[8]>(&v[c]));
                 tmem_wait_ld();
                 tc_fence_before();
-                mbar_arrive(&bar_qe[t * 3 + buf]);   // values are in registers: the issuer may reuse the buffer
+                arrive_issuer(&bar_qe[t * 3 + buf]);   // values are in registers: the issuer may reuse the buffer
 #pragma unroll
                 for (int j = 0; j < HC / 16; j++) {
                     uint4 o;
@@ -523,7 +636,11 @@ post_attn_kernel(const PostAttnArgs a)
     if (threadIdx.x == 0) MG_STAMP(91);
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc<K::TMEM_COLS>(tmem);
+    if (PAIR) cluster_sync_all();         // no CTA leaves (or frees TMEM) while the pair's UMMAs / commits may still target it
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_dealloc_pair<K::TMEM_COLS>(tmem);
+        else tmem_dealloc<K::TMEM_COLS>(tmem);
+    }
 }
 
 // embedding + ln_1 of block 0 in one pass (model.py:171-175 + model.py:102): X_ti and A_ti out.
