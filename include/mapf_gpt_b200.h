@@ -181,7 +181,8 @@ int mg_test_attention(int device, const void *q, const void *k, const void *v, v
 int mg_test_gemm_time(int device, int M, int N, int K, int BN, int iters, float *ms);
 /* pure UMMA rate: one thread issues iters*4 UMMAs (M128 x N x K16) on smem-resident operands; cycles2 = {issue->done, issue loop} */
 int mg_test_umma_rate(int device, int N, int iters, int ctas, long long *cycles2);
-/* clock64() stamps of the first 4 CTAs of the last fused post-attention launch (profiling aid, out[4][128]) */
+/* profiling aid, out[17][128]: clock64() stamps of 4 CTAs of the last fused post-attention / attention launch (rows 0-3),
+ * per-CTA attention load-balance data (rows 4-15), phase-cycle accumulators of -DMG_PHASE_PROF builds (row 16) */
 int mg_test_timeline(mg_engine *e, int enable, long long *out);
 
 #ifdef __cplusplus

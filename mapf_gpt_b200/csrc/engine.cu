@@ -1316,12 +1316,12 @@ int mg_test_timeline(mg_engine *e, int enable, long long *out)
     if (!e) return fail(MG_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     if (enable && !e->d_timeline) {
-        CU(dalloc(&e->d_timeline, 16 * 128));
-        CU(cudaMemset(e->d_timeline, 0, 16 * 128 * 8));
+        CU(dalloc(&e->d_timeline, 17 * 128));
+        CU(cudaMemset(e->d_timeline, 0, 17 * 128 * 8));
     }
     if (out && e->d_timeline) {
         CU(cudaStreamSynchronize(e->stream));
-        CU(cudaMemcpy(out, e->d_timeline, 16 * 128 * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out, e->d_timeline, 17 * 128 * 8, cudaMemcpyDeviceToHost));
     }
     if (!enable && e->d_timeline) { cudaFree(e->d_timeline); e->d_timeline = nullptr; }
     return MG_OK;

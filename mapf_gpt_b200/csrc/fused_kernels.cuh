@@ -43,6 +43,22 @@ struct PostAttnArgs {
         if (a.timeline != nullptr && (blockIdx.x - MG_STAMP_CTA0) < 4u) a.timeline[(blockIdx.x - MG_STAMP_CTA0) * 128 + (id)] = clock64(); \
     } while (0)
 
+// Phase profile (builds with -DMG_PHASE_PROF only, tools/phase_profile.py): cycles per phase summed over ALL CTAs of every
+// launch into timeline[2048 + id] -- worker thread 0 (ids 0..15) and the UMMA issuer's lane 0 (ids 20..25).
+#ifdef MG_PHASE_PROF
+#define MG_LAP(id)                                                                                     \
+    do {                                                                                               \
+        if (a.timeline != nullptr) {                                                                   \
+            const long long now_ = clock64();                                                          \
+            atomicAdd(reinterpret_cast<unsigned long long *>(a.timeline) + 2048 + (id), (unsigned long long)(now_ - lap_t)); \
+            lap_t = now_;                                                                              \
+        }                                                                                              \
+    } while (0)
+#define MG_LAP_INIT long long lap_t = clock64()
+#else
+#define MG_LAP(id) do { } while (0)
+#define MG_LAP_INIT do { } while (0)
+#endif
 // (v - mean) * rstd * gain for 8 consecutive columns -> 8 bf16 (one 16-byte store); a = rstd, b = -mean * rstd
 __device__ __forceinline__ uint4 ln_pack8(const uint32_t *v, f32x2 a, f32x2 b, const float4 g0, const float4 g1)
 {
@@ -295,11 +311,14 @@ post_attn_kernel(const PostAttnArgs a)
             constexpr uint32_t idescH = umma_idesc_bf16(UM, HC, 0, 0);
             const uint32_t a_addr = smem_u32(As), h_addr = smem_u32(Hs), r_addr = smem_u32(ring);
             int i = 0;  // stage cursor
+            MG_LAP_INIT;
             auto stage_wait = [&](int idx) -> uint32_t {
                 const int s = idx % S;
+                if (lane == 0) MG_LAP(21);                   // issue + waits on the workers since the last lap
                 mbar_wait(&full[s], (idx / S) & 1);
                 if (PAIR) mbar_wait(&pfull[s], (idx / S) & 1);
                 tc_fence_after();
+                if (lane == 0) MG_LAP(20);                   // waiting for the weight ring
                 return r_addr + s * K::SLOT_BYTES;
             };
             // proj: acc_main (pre-loaded with x) += att @ Wproj^T
@@ -310,6 +329,7 @@ post_attn_kernel(const PostAttnArgs a)
                 mbar_wait(&bar_x[t], 0);
             }
             tc_fence_after();
+            if (lane == 0) MG_LAP(22);                       // att tile + residual pre-load
             if (elect_one()) MG_STAMP(1);
             __syncwarp();
             for (int st = 0; st < K::NPROJ / U; st++, i++) {
@@ -426,6 +446,7 @@ post_attn_kernel(const PostAttnArgs a)
                 if (elect_one()) MG_STAMP(41);
                 __syncwarp();
             }
+            if (lane == 0) MG_LAP(21);
         }
     } else {
         // ------------------------------------------------------------------ workers (256 threads per tile)
@@ -439,6 +460,8 @@ post_attn_kernel(const PostAttnArgs a)
         const float inv_c = 1.0f / (float)C;
         const uint32_t nb = 1 + t;                        // named barrier of this tile's 256 workers
         float4 *Xg = reinterpret_cast<float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
+        MG_LAP_INIT;
+#define MG_WLAP(id) do { if (threadIdx.x == 0) MG_LAP(id); } while (0)
 
         // ---- x -> TMEM accumulator (overlaps the att tile load); c_proj then accumulates onto it.
         // All loads are issued before the first TMEM store so the thread pays ONE memory round trip.
@@ -457,10 +480,12 @@ post_attn_kernel(const PostAttnArgs a)
         tmem_wait_st();
         tc_fence_before();
         arrive_issuer(&bar_x[t]);
+        MG_WLAP(0);      // residual tile -> TMEM
 
         // ---- epilogue 1: LN2(x1) -> A tile (x1 = x + proj stays in TMEM)
         mbar_wait(bar_proj, 0);
         tc_fence_after();
+        MG_WLAP(1);      // waiting for att tile + c_proj
         if (threadIdx.x == 0) MG_STAMP(50);
         {
             f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
@@ -503,6 +528,7 @@ post_attn_kernel(const PostAttnArgs a)
             tc_fence_before();
             fence_proxy_async_smem();
             arrive_issuer(&bar_ln2[t]);
+            MG_WLAP(2);  // LN2
             if (threadIdx.x == 0) MG_STAMP(52);
         }
 
@@ -510,10 +536,14 @@ post_attn_kernel(const PostAttnArgs a)
         constexpr int HH = HC / 2;            // hidden columns per thread per chunk
         constexpr int NV = HH / 8;            // 16-byte groups
         uint8_t *Hb = Hs + t * K::H_BYTES;
+        // (Issuing the TMEM reads of chunk j+1 before chunk j's hidden values are stored -- a register ping-pong software
+        // pipeline -- was measured SLOWER, 2.18 vs 1.80 ms per launch: it needs 40 more live registers under the 96-register
+        // cap and delays the hidden-chunk hand-off whenever FC(j+1) is late.  Same for the q/k/v drain below.)
 #pragma unroll 1
         for (int j = 0; j < K::NCH; j++) {
             mbar_wait(&bar_a1f[t], j & 1);
             tc_fence_after();
+            MG_WLAP(3);  // waiting for the FC chunk
             if (threadIdx.x == 0) MG_STAMP(60 + 3 * j);
             uint32_t v[NV][8];
 #pragma unroll
@@ -521,6 +551,7 @@ post_attn_kernel(const PostAttnArgs a)
             tmem_wait_ld();
             tc_fence_before();
             arrive_issuer(&bar_a1e[t]);
+            MG_WLAP(4);  // FC chunk -> registers
             if (threadIdx.x == 0) MG_STAMP(61 + 3 * j);
             uint4 o[NV];
 #pragma unroll
@@ -530,17 +561,21 @@ post_attn_kernel(const PostAttnArgs a)
                 o[g].z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
                 o[g].w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
             }
+            MG_WLAP(5);  // GELU
             if (j >= 1) mbar_wait(&bar_he[t], (j - 1) & 1);       // proj2(j-1) has finished reading the buffer
+            MG_WLAP(6);  // waiting for the hidden buffer
 #pragma unroll
             for (int g = 0; g < NV; g++) *reinterpret_cast<uint4 *>(Hb + ((h * NV + g) * 128 + r) * 16) = o[g];
             fence_proxy_async_smem();
             arrive_issuer(&bar_hf[t]);
+            MG_WLAP(7);  // hidden chunk -> smem
             if (threadIdx.x == 0) MG_STAMP(62 + 3 * j);
         }
 
         // ---- final epilogue: x' -> HBM, xn = LN1_next(x') -> HBM
         mbar_wait(bar_done, 0);
         tc_fence_after();
+        MG_WLAP(8);      // waiting for the last proj2
         if (threadIdx.x == 0) MG_STAMP(90);
         {
             f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
@@ -560,6 +595,7 @@ post_attn_kernel(const PostAttnArgs a)
                 }
             };
             MG_COL_BATCHES(HALF, store_x);
+            MG_WLAP(9);  // x' -> HBM + statistics
             if (threadIdx.x == 0) MG_STAMP(92);
             if (a.xn_out != nullptr || fuse_qkv) {
                 {
@@ -605,6 +641,7 @@ post_attn_kernel(const PostAttnArgs a)
             tc_fence_before();
             fence_proxy_async_smem();
             arrive_issuer(&bar_qa[t]);
+            MG_WLAP(10); // LN1_next -> smem
             if (threadIdx.x == 0) MG_STAMP(93);
             const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
             uint4 *Oseq = reinterpret_cast<uint4 *>(a.qkv_out) + (size_t)seq * (3 * C / 8) * 256 + tok;
@@ -614,6 +651,7 @@ post_attn_kernel(const PostAttnArgs a)
                 const uint32_t col = (buf == 0 ? C : (buf == 1 ? 0 : HC)) + h * (HC / 2);
                 mbar_wait(&bar_qf[t * 3 + buf], (hh / 3) & 1);
                 tc_fence_after();
+                MG_WLAP(11);  // waiting for a q/k/v half-tile
                 if (threadIdx.x == 0) MG_STAMP(94 + hh);
                 uint32_t v[HC / 2];
 #pragma unroll
@@ -630,8 +668,10 @@ post_attn_kernel(const PostAttnArgs a)
                     o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
                     Oseq[qkv_off[(hh * HC + h * (HC / 2)) / 8 + j]] = o;
                 }
+                MG_WLAP(12);  // q/k/v half-tile -> HBM
             }
         }
+        MG_WLAP(13);
     }
     if (threadIdx.x == 0) MG_STAMP(91);
     tc_fence_before();

@@ -247,13 +247,16 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr)
 {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
-// arrive on the mbarrier at the same CTA-relative offset in CTA `cta` of this cluster
+// arrive on the mbarrier at the same CTA-relative offset in CTA `cta` of this cluster.  Default semantics (release at CTA
+// scope), as CUTLASS's ClusterBarrier::arrive(cta_id): a cluster-scope release costs the arriving warp ~1k cycles (measured
+// with tools/phase_profile.py), and what has to be ordered before the arrive is ordered by the fences the callers execute
+// themselves (fence.proxy.async for smem operand writes, tcgen05.fence::before_thread_sync for TMEM accesses).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
 {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)), "r"(cta)
         : "memory");
 }

@@ -16,9 +16,9 @@ eng.synchronize()
 print("kernel times of this single forward (cold clocks, no sustained power cap):",
       {k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in eng.kernel_times().items() if v["launches"]})
 eng.set_profiling(False)
-out = np.zeros((16, 128), np.int64)
+out = np.zeros((17, 128), np.int64)
 L.mg_test_timeline(eng._h, 0, out.ctypes.data_as(C.c_void_p))
-names = {0: "mma:start", 1: "mma:att ready", 2: "mma:proj issued", 3: "mma:ln2 ready", 40: "mma:all issued",
+names = {0: "mma:start", 1: "mma:att ready", 2: "mma:proj issued", 3: "mma:FC(0) stage landed", 4: "mma:ln2 seen", 5: "prod:refill S issued", 6: "prod:refill S+1 issued", 40: "mma:all issued",
          50: "wrk:proj done", 51: "wrk:epi1 pass1", 52: "wrk:ln2 arrive", 90: "wrk:done seen", 91: "wrk:end"}
 names.update({100: "att:start", 101: "att:QK landed", 102: "att:P+V ready", 103: "att:PV issued", 110: "att:S seen",
               111: "att:max done", 112: "att:P arrive", 113: "att:O seen", 114: "att:end"})
