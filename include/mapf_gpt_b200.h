@@ -53,7 +53,9 @@ typedef struct mg_params {
     int32_t obs_radius;            /* 5  */
     int32_t agents_radius;         /* 5  */
     int32_t grid_step;             /* 64 */
-    int32_t save_cost2go;          /* bool; the .bin cache (cpp:62-80) is not implemented: must be 0 */
+    int32_t save_cost2go;          /* bool; "precomputed_cost2go.bin" in the working directory (cpp:62-80,114-131): loaded when
+                                    * present, written after the computation otherwise.  Only maps wider than 74 padded cells
+                                    * have such a table here; a table of the wrong shape is an MG_ERR_ARG, not silently used */
 } mg_params;
 
 /* GPTConfig, mapf_gpt/model.py:107-115 (dropout must be 0, bias must be false) */

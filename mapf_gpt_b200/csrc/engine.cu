@@ -222,7 +222,7 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
 }
 
 #ifndef MG_POST_CL_DEFAULT
-#define MG_POST_CL_DEFAULT 1
+#define MG_POST_CL_DEFAULT 2
 #endif
 template <int C, int NT, int UU = 0, int CL = 1>
 static int launch_post_attn_c(mg_engine *e, PostAttnArgs a, int MT, int kc)
@@ -260,7 +260,9 @@ static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT, 
 {
     // NT = 1 (two CTAs per SM) measured faster than NT = 2 (one CTA per SM, shared weight stages): with one CTA per SM
     // the HBM phases (tile load / store) and the compute phase of an SM do not overlap.  MAPF_GPT_B200_POST_NT=2 selects it.
-    // MAPF_GPT_B200_POST_CL = 2: CTA pairs (cta_group::2 UMMAs, each SM streams half of the weights); needs an even tile count.
+    // Default: CTA pairs (cta_group::2 UMMAs, each SM streams half of the weights) whenever the tile count is even; measured
+    // +1 % on the whole step over single CTAs (less L2 traffic -> higher clocks under the power cap).  MAPF_GPT_B200_POST_CL=1
+    // selects single CTAs.
     static const int nt_override = getenv("MAPF_GPT_B200_POST_NT") ? atoi(getenv("MAPF_GPT_B200_POST_NT")) : 0;
     static const int cl_req = getenv("MAPF_GPT_B200_POST_CL") ? atoi(getenv("MAPF_GPT_B200_POST_CL")) : MG_POST_CL_DEFAULT;
     const int kc = single_tiles ? KC_POST_LAST : KC_POST;
@@ -550,18 +552,48 @@ static int add_large_map(mg_engine *e, const uint8_t *grid_pitched, int *slot_ou
     const int K = (int)list.size();
     uint16_t *pre = nullptr;
     CU(dalloc(&pre, (size_t)std::max(K, 1) * std::max(K, 1)));
+    // save_cost2go (cpp:62-80): "precomputed_cost2go.bin" in the working directory replaces the computation when present.
+    // Format: size_t rows, size_t cols, rows x cols uint16 (row = source cell, in precomputed_cells_map order).  The
+    // reference loads whatever it finds; a table whose shape does not fit this map is rejected here instead of being used.
+    bool loaded = false;
+    if (e->params.save_cost2go && K > 0) {
+        if (FILE *f = fopen("precomputed_cost2go.bin", "rb")) {
+            size_t dims[2] = {0, 0};
+            std::vector<uint16_t> tab((size_t)K * K);
+            const bool ok = fread(dims, sizeof(size_t), 2, f) == 2 && dims[0] == (size_t)K && dims[1] == (size_t)K &&
+                            fread(tab.data(), 2, tab.size(), f) == tab.size();
+            fclose(f);
+            if (!ok) {
+                cudaFree(pre);
+                return fail(MG_ERR_ARG, "precomputed_cost2go.bin holds a %zu x %zu table, this map needs %d x %d: stale cache "
+                                        "(the reference would use it unchecked, cpp:62-80)", dims[0], dims[1], K, K);
+            }
+            CU(cudaMemcpy(pre, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
+            loaded = true;
+        }
+    }
     uint8_t *d_grid = nullptr, *scratch = nullptr;
     int32_t *d_list = nullptr;
     CU(dalloc(&d_grid, cells));
     CU(dalloc(&d_list, (size_t)std::max(K, 1)));
     CU(cudaMemcpy(d_grid, grid_pitched, cells, cudaMemcpyHostToDevice));
-    if (K > 0) {
+    if (K > 0 && !loaded) {
         CU(cudaMemcpy(d_list, list.data(), (size_t)K * 4, cudaMemcpyHostToDevice));
         const int blocks = std::min(K, 2 * e->n_sms);
         CU(dalloc(&scratch, (size_t)blocks * (cells * 10 + 64)));
         e->launches++;
         precompute_kernel<<<blocks, 256, 0, e->stream>>>(d_grid, s.H, s.W, s.P, d_list, K, pre, scratch);
         CU(cudaStreamSynchronize(e->stream));
+        if (e->params.save_cost2go) {   // cpp:114-131
+            std::vector<uint16_t> tab((size_t)K * K);
+            CU(cudaMemcpy(tab.data(), pre, tab.size() * 2, cudaMemcpyDeviceToHost));
+            if (FILE *f = fopen("precomputed_cost2go.bin", "wb")) {   // like the reference, a file that cannot be opened is skipped
+                const size_t dims[2] = {(size_t)K, (size_t)K};
+                fwrite(dims, sizeof(size_t), 2, f);
+                fwrite(tab.data(), 2, tab.size(), f);
+                fclose(f);
+            }
+        }
     }
     cudaFree(scratch); cudaFree(d_grid); cudaFree(d_list);
     CU(cudaMemcpy(s.cell_idx + (size_t)slot * cells, cidx.data(), cells * 4, cudaMemcpyHostToDevice));
@@ -723,7 +755,6 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
                          "context 256, radius 5); the checkpoints fix it (inference.py:14-22)");
         return nullptr;
     }
-    if (p.save_cost2go) { fail(MG_ERR_ARG, "save_cost2go (precomputed_cost2go.bin cache) is not implemented"); return nullptr; }
     if (max_envs < 1 || max_agents < 1 || max_agents > 32767) { fail(MG_ERR_ARG, "bad capacity"); return nullptr; }
     if (H < 11 || W < 11 || H > 512 || W > 512) {
         fail(MG_ERR_ARG, "padded grid %dx%d unsupported: need 11..512 cells per side", H, W);

@@ -8,6 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 GOLD_OBS = np.load(Path(__file__).parent / "golden" / "obs_golden.npz")
 GOLD_GPT = np.load(Path(__file__).parent / "golden" / "gpt_golden.npz")
+GOLDEN = Path(__file__).parent / "golden"
 N_SCEN = len([k for k in GOLD_OBS.files if k.endswith("_tokens")])
 LOGIT_TOL = 5e-2   # bf16 operands, fp32 accumulate/residual vs the reference's fp32 (DESIGN.md "Tolerance")
 
@@ -316,3 +317,44 @@ def test_large_map_device_rollout(dev):
         ref[:, 125 + 10 * s_:130 + 10 * s_] = 0
     assert (tok == ref).all()
     eng.close()
+
+
+def test_cost2go_cache_file_matches_reference_and_reloads(dev, tmp_path, monkeypatch):
+    """save_cost2go (cpp:62-80,114-131): the engine writes precomputed_cost2go.bin byte-identical to the file the unmodified
+    reference writes for the same map (tests/golden/make_cache_golden.py), reloads it instead of recomputing (tokens stay
+    exact vs the oracle), and refuses a table of the wrong shape instead of using it."""
+    import hashlib, json, importlib.util
+    import oracle
+    from mapf_gpt_b200 import engine as E, maps, _lib
+    gold = json.loads((GOLDEN / "cost2go_cache_golden.json").read_text())
+    spec = importlib.util.spec_from_file_location("make_cache_golden", GOLDEN / "make_cache_golden.py")
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    grid = mk.cache_grid()
+    m = {"name": "cache", "grid": grid, "starts": np.zeros(grid.shape, bool), "goals": np.zeros(grid.shape, bool)}
+    n = 24
+    st, gl = maps.sample_instance(m, n, 3)
+    monkeypatch.chdir(tmp_path)
+    f = tmp_path / "precomputed_cost2go.bin"
+
+    def tokens(params):
+        eng = E.RolloutEngine(1, n, *grid.shape, params=params)
+        eng.reset(0, grid, st[None], gl[None])
+        eng.update_agents(None, None, None)
+        t = eng.generate_observations()[0]
+        eng.close()
+        return t
+
+    orc = oracle.ObsOracle(grid)
+    orc.create_agents(st, gl)
+    orc.update_agents(st, gl, np.full(n, -1, np.int32))
+    want = orc.generate_observations()
+    assert (tokens(None) == want).all() and not f.exists()            # default: no file is touched
+    assert (tokens({"save_cost2go": 1}) == want).all()
+    raw = f.read_bytes()
+    assert len(raw) == gold["bytes"] and hashlib.sha256(raw).hexdigest() == gold["sha256"]
+    stamp = f.stat().st_mtime_ns
+    assert (tokens({"save_cost2go": 1}) == want).all() and f.stat().st_mtime_ns == stamp   # loaded, not rewritten
+    f.write_bytes(np.array([3, 3], np.uint64).tobytes() + bytes(18))
+    with pytest.raises(_lib.MgError, match="stale cache"):
+        tokens({"save_cost2go": 1})
