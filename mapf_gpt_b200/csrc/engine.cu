@@ -55,6 +55,7 @@ struct Model {
     bool fuse_qkv = false;  // ... and the next block's c_attn
     float *wte = nullptr, *wpe = nullptr, *lnf = nullptr;
     float *wpe_ti = nullptr;   // wpe re-tiled [2][C/4][128][4] for embed_ln_kernel
+    uint4 *tab0 = nullptr;     // block 0 as a lookup: [67 tokens][256 positions][C/4 + 3C/8] 16-byte groups (x, then q|k|v)
     std::vector<Layer> layers;
 };
 struct Workspace {
@@ -425,12 +426,17 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         const int M = ns * 256, MT = M / 128;
         if (m.fused) {
             prof_begin(e, KC_EMBED);
-            embed_ln_kernel<<<MT, 128, 67 * (C + 4) * 4, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe_ti, m.layers[0].ln1,
-                                                                      w.X, w.XN, C);
+            if (m.tab0 && C == 160)
+                block0_lookup_kernel<160><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, w.X, w.QKV);
+            else if (m.tab0 && C == 256)
+                block0_lookup_kernel<256><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, w.X, w.QKV);
+            else
+                embed_ln_kernel<<<MT, 128, 67 * (C + 4) * 4, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe_ti, m.layers[0].ln1,
+                                                                          w.X, w.XN, C);
             prof_end(e);
             for (int l = 0; l < m.cfg.n_layer; l++) {
                 const Layer &L = m.layers[l];
-                if (l == 0 || !m.fuse_qkv) {   // blocks >= 1 get q/k/v from the previous block's fused kernel
+                if ((l == 0 && !m.tab0) || !m.fuse_qkv) {   // blocks >= 1 get q/k/v from the previous block's fused kernel
                     GemmArgs g{};
                     g.A = w.XN; g.W = L.wqkv; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
                     if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
@@ -852,7 +858,7 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(e->d_pos_in); cudaFree(e->d_goal_in); cudaFree(e->d_act_in); cudaFree(e->d_step_act); cudaFree(e->d_q);
     cudaFree(e->d_metrics);
     Model &m = e->model;
-    cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti);
+    cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti); cudaFree(m.tab0);
     for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); cudaFree(L.wstream_pair); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
@@ -936,6 +942,29 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         }
     }
     if ((rc = upload_f32(w, C, &m.lnf))) return rc;
+    if (m.fused && m.fuse_qkv && getenv("MAPF_GPT_B200_NO_BLOCK0_TABLE") == nullptr) {
+        // block 0 as a lookup (fused_kernels.cuh): run the production embedding + QKV kernels on 67 synthetic sequences
+        const int nseq = 67, M = nseq * 256, nrec = C / 4 + 3 * C / 8;
+        std::vector<uint8_t> tk((size_t)M);
+        for (int i = 0; i < nseq; i++) memset(tk.data() + (size_t)i * 256, i, 256);
+        uint8_t *d_tk = nullptr;
+        float *X = nullptr;
+        __nv_bfloat16 *XN = nullptr, *QKV = nullptr;
+        CU(dalloc(&d_tk, (size_t)M));
+        CU(dalloc(&X, (size_t)M * C));
+        CU(dalloc(&XN, (size_t)M * C));
+        CU(dalloc(&QKV, (size_t)M * 3 * C));
+        CU(dalloc(&m.tab0, (size_t)M * nrec));
+        CU(cudaMemcpyAsync(d_tk, tk.data(), tk.size(), cudaMemcpyHostToDevice, e->stream));
+        embed_ln_kernel<<<M / 128, 128, 67 * (C + 4) * 4, e->stream>>>(d_tk, m.wte, m.wpe_ti, m.layers[0].ln1, X, XN, C);
+        GemmArgs g{};
+        g.A = XN; g.W = m.layers[0].wqkv; g.out = QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = cfg->n_head; g.hs = m.hs;
+        if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
+        block0_table_kernel<<<M / 128, 128, 0, e->stream>>>(X, QKV, m.tab0, C);
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaGetLastError());
+        cudaFree(d_tk); cudaFree(X); cudaFree(XN); cudaFree(QKV);
+    }
     m.loaded = true;
     return MG_OK;
 }

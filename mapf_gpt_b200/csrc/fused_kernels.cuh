@@ -586,8 +586,8 @@ post_attn_kernel(const PostAttnArgs a)
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < N / 4; j++) {
-                    Xg[(size_t)((h * HALF + C0) / 4 + j) * 128] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
-                                                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    __stcs(&Xg[(size_t)((h * HALF + C0) / 4 + j) * 128], make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
+                                                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     const f32x2 e0 = pk2u(v[4 * j + 0], v[4 * j + 1]), e1 = pk2u(v[4 * j + 2], v[4 * j + 3]);
                     sum2 = add2(sum2, add2(e0, e1));
                     sq2 = fma2(e0, e0, sq2);
@@ -666,7 +666,7 @@ post_attn_kernel(const PostAttnArgs a)
                     o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
                     o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
                     o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                    Oseq[qkv_off[(hh * HC + h * (HC / 2)) / 8 + j]] = o;
+                    __stcs(&Oseq[qkv_off[(hh * HC + h * (HC / 2)) / 8 + j]], o);   // streaming: 3.4 GB per launch pass through L2 once
                 }
                 MG_WLAP(12);  // q/k/v half-tile -> HBM
             }
@@ -729,6 +729,91 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(const uint8_t *__restrict
         o.z = pack_bf16x2((t1.x + p1.x - mean) * rstd * g1.x, (t1.y + p1.y - mean) * rstd * g1.y);
         o.w = pack_bf16x2((t1.z + p1.z - mean) * rstd * g1.z, (t1.w + p1.w - mean) * rstd * g1.w);
         O[(size_t)c8 * 128] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block 0 as a lookup.  x = wte[token] + wpe[position] (model.py:171-175) depends only on (token id, position), and so do
+// ln_1(x) and q/k/v = ln_1(x) @ Wqkv^T of block 0 (model.py:102,50): 67 x 256 combinations.  At model load the engine runs
+// embed_ln_kernel + the QKV GEMM once on 67 synthetic sequences (sequence i = token i at every position), i.e. through the
+// SAME kernels, so the looked-up values are bit-identical to the computed ones; the table (one record of C fp32 + 3C bf16 per
+// combination, 27 MB at C = 160) stays L2-resident.  Per timestep block 0 is then a pure HBM-write-bound gather:
+// 4C + 6C bytes per token out, no GEMM, no xn round trip.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) block0_table_kernel(const float *__restrict__ X, const __nv_bfloat16 *__restrict__ QKV,
+                                                           uint4 *__restrict__ tab, int C)
+{
+    const int mt = blockIdx.x, r = threadIdx.x, tok = mt >> 1, t = ((mt & 1) << 7) + r;
+    const int nx = C / 4, nq = 3 * C / 8;
+    uint4 *rec = tab + ((size_t)tok * 256 + t) * (nx + nq);
+    const uint4 *X4 = reinterpret_cast<const uint4 *>(X) + (size_t)mt * nx * 128 + r;
+    const uint4 *Q4 = reinterpret_cast<const uint4 *>(QKV) + (size_t)tok * nq * 256 + t;
+    for (int g = 0; g < nx; g++) rec[g] = X4[(size_t)g * 128];
+    for (int g = 0; g < nq; g++) rec[nx + g] = Q4[(size_t)g * 256];
+}
+// The table must stay in L2 while 3.4 GB of output stream through it: table reads carry an evict_last L2 policy, output
+// stores are streaming (evict_first).
+#ifndef MG_LOOKUP_PLAIN
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_keep_l2(const uint4 *p, uint64_t policy)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) { __stcs(p, v); }
+#else
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
+__device__ __forceinline__ uint4 ld_keep_l2(const uint4 *p, uint64_t) { return __ldg(p); }
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) { *p = v; }
+#endif
+// One block per 128-token tile.  Records are read the way they lie in memory (consecutive threads read consecutive 16-byte
+// groups of one record: a warp-level load touches 2-4 contiguous segments instead of 32 lines), transposed through shared
+// memory (row pitch CH + 1 groups: conflict-free 16-byte accesses), and written token-major (512 contiguous bytes per warp).
+template <int C>
+__global__ void __launch_bounds__(128) block0_lookup_kernel(const uint8_t *__restrict__ tokens, const uint4 *__restrict__ tab,
+                                                            float *__restrict__ X, __nv_bfloat16 *__restrict__ QKV)
+{
+    constexpr int NX = C / 4, NQ = 3 * C / 8, NREC = NX + NQ;
+    constexpr int CH = C == 160 ? 10 : 8, PITCH = CH + 1;       // groups per pass; NX and NQ are multiples of CH
+    static_assert(NX % CH == 0 && NQ % CH == 0, "block0_lookup_kernel: chunking");
+    __shared__ uint4 S[128 * PITCH];
+    __shared__ int rec_of[128];
+    const uint64_t keep = l2_policy_evict_last();
+    const int mt = blockIdx.x, r = threadIdx.x, seq = mt >> 1, t = ((mt & 1) << 7) + r;
+    rec_of[r] = (min((int)tokens[(size_t)mt * 128 + r], 66) * 256 + t) * NREC;
+    uint4 *X4 = reinterpret_cast<uint4 *>(X) + (size_t)mt * NX * 128 + r;
+    uint4 *Q4 = reinterpret_cast<uint4 *>(QKV) + (size_t)seq * NQ * 256 + t;
+    __syncthreads();
+#pragma unroll 1
+    for (int g0 = 0; g0 < NREC; g0 += CH) {
+        uint4 v[CH];
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const int f = k * 128 + r, tk = f / CH, gg = f - tk * CH;
+            v[k] = ld_keep_l2(tab + rec_of[tk] + g0 + gg, keep);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const int f = k * 128 + r, tk = f / CH, gg = f - tk * CH;
+            S[tk * PITCH + gg] = v[k];
+        }
+        __syncthreads();
+        if (g0 < NX) {
+#pragma unroll
+            for (int gg = 0; gg < CH; gg++) st_stream(X4 + (size_t)(g0 + gg) * 128, S[r * PITCH + gg]);
+        } else {
+#pragma unroll
+            for (int gg = 0; gg < CH; gg++) st_stream(Q4 + (size_t)(g0 - NX + gg) * 256, S[r * PITCH + gg]);
+        }
+        __syncthreads();
     }
 }
 

@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                     o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
                     const int col = head * HS + kh * 16 + 8 * j;
                     uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
-                    *O = o;
+                    __stcs(O, o);
                 }
                 if (stamp) MG_ASTAMP(115 + 8 * qt);
             }

@@ -218,6 +218,26 @@ def test_fused_and_generic_paths_agree(dev, name, monkeypatch):
     assert np.abs(outs[0] - ref).max() < LOGIT_TOL and np.abs(outs[1] - ref).max() < LOGIT_TOL
 
 
+@pytest.mark.parametrize("name", ["2M", "6M"])
+def test_block0_lookup_table_is_bit_identical_to_the_computed_block0(dev, name, monkeypatch):
+    """Block 0's embedding + ln_1 + c_attn depend only on (token, position): the engine tabulates them at model load through
+    the same kernels; logits must not change by a single bit, and every (token, position) pair is exercised."""
+    from mapf_gpt_b200 import engine as E, weights as W
+    cfg = W.model_config(name)
+    sd = W.scale_weights(W.perturb_layernorm(W.random_init(cfg)), 3.0)
+    rng = np.random.default_rng(5)
+    toks = np.concatenate([np.repeat(np.arange(67, dtype=np.int8)[:, None], 256, 1),      # every (token, position) pair
+                           rng.integers(0, 67, (61, 256)).astype(np.int8)])
+    outs = []
+    for off in (None, "1"):
+        if off: monkeypatch.setenv("MAPF_GPT_B200_NO_BLOCK0_TABLE", off)
+        eng = E.RolloutEngine(1, 1, 11, 11)
+        eng.load_model(sd, cfg)
+        outs.append(eng.forward_tokens(toks))
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
 # ------------------------------------------------------------------------------------------------ large maps (SURVEY 8f.1)
 def _big_grid(seed=0, h=150, w=170, p=0.18):
     from mapf_gpt_b200 import maps
