@@ -40,12 +40,15 @@ def flops_per_agent_step(L, C, T=256, V=67):
     return L * (24 * T * C * C + 4 * T * T * C) + 2 * C * V
 
 
-def flops_executed(L, C, T=256, V=67, pruned=True):
+def flops_executed(L, C, T=256, V=67, pruned=True, block0_table=False):
     """What the kernels execute: with last-block pruning the last block runs attention for one
-    query and c_proj + MLP for one token per sequence (its QKV GEMM still covers all tokens)."""
+    query and c_proj + MLP for one token per sequence (its QKV GEMM still covers all tokens); with block 0 tabulated
+    per (token, position) at model load its c_attn GEMM (6 T C^2) is a lookup, not arithmetic."""
     f = flops_per_agent_step(L, C, T, V)
     if pruned:
         f -= (4 * T * T * C - 4 * T * C) + 18 * C * C * (T - 1)
+    if block0_table:
+        f -= 6 * T * C * C
     return f
 
 
@@ -254,13 +257,14 @@ def main():
         pk = peaks()
         F = flops_per_agent_step(cfg.n_layer, cfg.n_embd)
         pruned = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1"
-        Fx = flops_executed(cfg.n_layer, cfg.n_embd, pruned=pruned)
+        fuse_qkv = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
+        table0 = fuse_qkv and os.environ.get("MAPF_GPT_B200_NO_BLOCK0_TABLE") is None
+        Fx = flops_executed(cfg.n_layer, cfg.n_embd, pruned=pruned, block0_table=table0)
         C, L, T = cfg.n_embd, cfg.n_layer, 256
         rows_per_launch = min(E_gpu * n, 8192) * T           # the engine forwards in chunks of 8192 sequences
         kflops = {"gemm_qkv": 2 * 3 * C * C, "gemm_attn_proj": 2 * C * C, "gemm_fc_gelu": 2 * 4 * C * C,
                   "gemm_mlp_proj": 2 * 4 * C * C, "attention": 4 * T * C,
                   "post_attn_fused": 2 * 9 * C * C}   # per token
-        fuse_qkv = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
         if fuse_qkv:
             kflops["post_attn_fused"] += 2 * 3 * C * C       # + the next block's c_attn
         kern = {}
@@ -288,7 +292,7 @@ def main():
                          "whole_step_tflops": round(value / world * Fx / 1e12, 1),
                          "whole_step_frac": round(value / world * Fx / 1e12 / pk["tflops"], 4),
                          "flops_per_agent_step_executed": Fx, "flops_per_agent_step_reference": F,
-                         "last_block_pruned": pruned},
+                         "last_block_pruned": pruned, "block0_lookup_table": table0},
             "kernels": kern, "phases_ms_last_step": {"observe": phases[0], "forward": phases[1], "sample_step": phases[2]},
             "clocks": clocks,
             "episode_metrics_sum": {"envs": msum[0].item(), "CSR": msum[1].item(), "ISR": msum[2].item(),

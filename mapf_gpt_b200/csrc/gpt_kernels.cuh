@@ -273,6 +273,12 @@ __device__ __forceinline__ void exp2_poly2(f32x2 x, float &r0, float &r1)
     r1 = __uint_as_float(p1 + (t1 << 23));
 }
 
+// which of the 16 pairs of a 32-column group take the polynomial instead of MUFU.EX2: (j & MASK) == MASK
+// (1: every other pair, 3: every fourth, 16: none).  The kernel is issue-bound (62 % issue-active, XU 39 %): a polynomial
+// pair costs ~14 issue slots, a MUFU pair ~5.  Measured per launch: 50 % poly 0.982 ms, 25 % 0.954-0.971, 12.5 % 0.995, 0 % 1.074.
+#ifndef MG_ATTN_POLY_MASK
+#define MG_ATTN_POLY_MASK 3
+#endif
 __device__ __forceinline__ float max3(float a, float b, float c)
 {
     float r;
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                     for (int j = 0; j < 16; j++) {
                         const f32x2 xs = fma2(pk2u(v[2 * j], v[2 * j + 1]), sc2, mo2);
                         float e0, e1;
-                        if (j & 1) {
+                        if ((j & MG_ATTN_POLY_MASK) == MG_ATTN_POLY_MASK) {
                             exp2_poly2(xs, e0, e1);
                         } else {
                             upk2(xs, e0, e1);
