@@ -129,7 +129,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, envs),
+            "config": workload_config(args, args.envs),     # the workload; each step of this arm is a bounded sample of it
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": r.kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "torch_threads": torch.get_num_threads()}
@@ -154,8 +154,8 @@ def main():
     ap.add_argument("--map", default="validation-mazes-seed-000")
     ap.add_argument("--agents", type=int, default=64)
     ap.add_argument("--envs", type=int, default=1024, help="envs per GPU")
-    ap.add_argument("--ref-envs", type=int, default=1, help="envs in the CPU sample (--impl reference / cpu_baseline)")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--ref-envs", type=int, default=8, help="envs in the CPU sample (--impl reference / cpu_baseline)")
+    ap.add_argument("--cpu-steps", type=int, default=12, help="timesteps of the cpu_baseline sample (~10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no e2e / cpu baseline, warm-up as given")
@@ -267,7 +267,10 @@ def main():
                   "post_attn_fused": 2 * 9 * C * C}   # per token
         if fuse_qkv:
             kflops["post_attn_fused"] += 2 * 3 * C * C       # + the next block's c_attn
+        kbytes = {"block0_lookup": 10 * C, "embed": 6 * C, "attention_last_token": 4 * C}
         kern = {}
+        if table0 and "embed" in ktimes:       # block 0 runs as the (token, position) lookup, not embedding + LN + GEMM
+            ktimes = {("block0_lookup" if k == "embed" else k): v for k, v in ktimes.items()}
         for k, v in ktimes.items():
             if v["launches"]:
                 avg = v["ms"] / v["launches"]
@@ -275,6 +278,9 @@ def main():
                        "share": round(v["ms"] / total_ms, 4)}
                 if k in kflops:
                     ent["tflops"] = round(kflops[k] * rows_per_launch / (avg * 1e-3) / 1e12, 1)
+                if k in kbytes:     # HBM-bound kernels: algorithmic bytes per token against the measured copy peak
+                    ent["hbm_gbs"] = round(kbytes[k] * rows_per_launch / (avg * 1e-3) / 1e9, 1)
+                    ent["hbm_frac"] = round(ent["hbm_gbs"] / pk["hbm_gbs"], 3)
                 kern[k] = ent
         dom = max((k for k in kern if k in kflops), key=lambda k: kern[k]["ms_total"])
         achieved = kern[dom]["tflops"]
