@@ -598,6 +598,9 @@ post_attn_kernel(const PostAttnArgs a)
             MG_WLAP(9);  // x' -> HBM + statistics
             if (threadIdx.x == 0) MG_STAMP(92);
             if (a.xn_out != nullptr || fuse_qkv) {
+                // the scratch was last read in the LN2 epilogue; every worker has long passed that point (the mbarrier chain of
+                // the MLP phase orders it), the barrier states it in a form compute-sanitizer's racecheck can follow
+                named_bar_sync(nb, 256);
                 {
                     float s0, s1, q0, q1;
                     upk2(sum2, s0, s1);
