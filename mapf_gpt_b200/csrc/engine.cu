@@ -44,6 +44,7 @@ enum KernelClass { KC_BFS = 0, KC_OBSERVE, KC_EMBED, KC_LN, KC_QKV, KC_ATTN, KC_
 struct Layer {
     float *ln1 = nullptr, *ln2 = nullptr;
     __nv_bfloat16 *wqkv = nullptr, *wproj = nullptr, *wfc = nullptr, *wproj2 = nullptr;
+    __nv_bfloat16 *wqkv_p = nullptr, *wproj_p = nullptr, *wfc_p = nullptr, *wproj2_p = nullptr;   // CTA-pair packing (generic path, BN = 256)
     __nv_bfloat16 *wstream = nullptr;   // fused post-attention kernel: stage images in consumption order
     __nv_bfloat16 *wstream_pair = nullptr;   // the same stream for CTA pairs: every stage split into two N/2-row halves
 };
@@ -164,6 +165,21 @@ static int upload_f32(const float *src, size_t n, float **out)
 {
     CU(dalloc(out, n));
     CU(cudaMemcpy(*out, src, n * 4, cudaMemcpyHostToDevice));
+    return MG_OK;
+}
+
+// the same for gemm_pair_kernel: [N/BN][2 halves][K/8][BN/2][8], CTA r of a pair streams rows [r * BN/2, (r+1) * BN/2) of the tile
+static int upload_packed_pair(const float *W, int N, int K, int BN, __nv_bfloat16 **out)
+{
+    std::vector<uint16_t> h((size_t)N * K);
+    const int HB = BN / 2;
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++) {
+            const int nt = n / BN, nn = n % BN, half = nn / HB, hn = nn % HB;
+            h[((((size_t)nt * 2 + half) * (K / 8) + k / 8) * HB + hn) * 8 + (k & 7)] = f2bf(W[(size_t)n * K + k]);
+        }
+    CU(dalloc(out, (size_t)N * K));
+    CU(cudaMemcpy(*out, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
     return MG_OK;
 }
 
@@ -296,9 +312,42 @@ static int launch_gemm_cfg(mg_engine *e, const GemmArgs &a, int kc)
     return MG_OK;
 }
 template <int EPI>
+static int launch_gemm_pair(mg_engine *e, const GemmArgs &a, int kc)
+{
+    constexpr int BN = 256, BK = 64, STAGES = 3;
+    constexpr int smem = gemm_pair_smem_bytes<BN, BK, STAGES>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(gemm_pair_kernel<BN, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((a.M / 128) * (a.N / BN));
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    prof_begin(e, kc);
+    CU(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN, BK, STAGES, EPI>, a));
+    prof_end(e);
+    CU(cudaGetLastError());
+    return MG_OK;
+}
+template <int EPI>
 static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 {
     if (a.M % 128) return fail(MG_ERR_ARG, "gemm: M=%d not a multiple of 128", a.M);
+    // CTA pairs (cta_group::2, gemm_pair_kernel) are OPT-IN (MAPF_GPT_B200_GEMM_PAIR=1): +6 % on the 85M step, parity-green, but two
+    // of six processes hung in their first forward on the GPU box (two CTA pairs co-resident per SM pair, 147k short-lived CTAs per
+    // launch; suspected tcgen05.alloc.cta_group::2 permit inversion).  Not shipped as a default until that is understood.
+    static const bool pair_on = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
+    if (e && a.Wp && pair_on && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI>(e, a, kc);
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
     if (BN == 256 && a.N % 256 == 0 && a.K % 64 == 0) return launch_gemm_cfg<256, 64, 2, EPI>(e, a, kc);
@@ -412,6 +461,15 @@ static int ensure_workspace(mg_engine *e, int want_seqs)
     return MG_OK;
 }
 
+static void launch_ln(mg_engine *e, const float *X, const float *gain, __nv_bfloat16 *out, int C, int MT)
+{
+    if (C == 768) ln_rows_kernel<24><<<MT * 4, 256, 0, e->stream>>>(X, gain, out);
+    else if (C == 512) ln_rows_kernel<16><<<MT * 4, 256, 0, e->stream>>>(X, gain, out);
+    else if (C == 256) ln_rows_kernel<8><<<MT * 4, 256, 0, e->stream>>>(X, gain, out);
+    else if (C == 128) ln_rows_kernel<4><<<MT * 4, 256, 0, e->stream>>>(X, gain, out);
+    else ln_kernel<<<MT, 128, 0, e->stream>>>(X, gain, out, C);
+}
+
 // tokens (device, uint8 [n_seq][256]) -> logits (device, fp32 [n_seq][8])
 static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float *logits)
 {
@@ -486,26 +544,26 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         for (int l = 0; l < m.cfg.n_layer; l++) {
             const Layer &L = m.layers[l];
             prof_begin(e, KC_LN);
-            ln_kernel<<<MT, 128, 0, e->stream>>>(w.X, L.ln1, w.XN, C);
+            launch_ln(e, w.X, L.ln1, w.XN, C, MT);
             prof_end(e);
             GemmArgs g{};
-            g.A = w.XN; g.W = L.wqkv; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
+            g.A = w.XN; g.W = L.wqkv; g.Wp = L.wqkv_p; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
             if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
             AttnArgs at{};
             at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
             at.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
             if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
             g = GemmArgs{};
-            g.A = w.ATT; g.W = L.wproj; g.out = w.X; g.M = M; g.N = C; g.K = C;
+            g.A = w.ATT; g.W = L.wproj; g.Wp = L.wproj_p; g.out = w.X; g.M = M; g.N = C; g.K = C;
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ))) return rc;
             prof_begin(e, KC_LN);
-            ln_kernel<<<MT, 128, 0, e->stream>>>(w.X, L.ln2, w.XN, C);
+            launch_ln(e, w.X, L.ln2, w.XN, C, MT);
             prof_end(e);
             g = GemmArgs{};
-            g.A = w.XN; g.W = L.wfc; g.out = w.HID; g.M = M; g.N = 4 * C; g.K = C;
+            g.A = w.XN; g.W = L.wfc; g.Wp = L.wfc_p; g.out = w.HID; g.M = M; g.N = 4 * C; g.K = C;
             if ((rc = launch_gemm<EPI_GELU>(e, m.BN, g, KC_FC))) return rc;
             g = GemmArgs{};
-            g.A = w.HID; g.W = L.wproj2; g.out = w.X; g.M = M; g.N = C; g.K = 4 * C;
+            g.A = w.HID; g.W = L.wproj2; g.Wp = L.wproj2_p; g.out = w.X; g.M = M; g.N = C; g.K = 4 * C;
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ2))) return rc;
         }
         prof_begin(e, KC_HEAD);
@@ -859,7 +917,8 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(e->d_metrics);
     Model &m = e->model;
     cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti); cudaFree(m.tab0);
-    for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); cudaFree(L.wstream_pair); }
+    for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); cudaFree(L.wstream_pair);
+                                cudaFree(L.wqkv_p); cudaFree(L.wproj_p); cudaFree(L.wfc_p); cudaFree(L.wproj2_p); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
     cudaFree(w.Xc); cudaFree(w.ATTc);
@@ -914,22 +973,27 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         const char *np = getenv("MAPF_GPT_B200_NO_PRUNE");
         e->prune_last = !(np && np[0] == '1');
     }
+    const bool pair_gemm = !m.fused && BN == 256 && getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;
         if ((rc = upload_packed(w, 3 * C, C, BN, &L.wqkv))) return rc;
+        if (pair_gemm && (rc = upload_packed_pair(w, 3 * C, C, BN, &L.wqkv_p))) return rc;
         w += 3 * CC;
         const float *wproj = w;
         if ((rc = upload_packed(w, C, C, BN, &L.wproj))) return rc;
+        if (pair_gemm && (rc = upload_packed_pair(w, C, C, BN, &L.wproj_p))) return rc;
         w += CC;
         const float *g2 = w;
         if ((rc = upload_f32(w, C, &L.ln2))) return rc;
         w += C;
         const float *wfc = w;
         if ((rc = upload_packed(w, 4 * C, C, BN, &L.wfc))) return rc;
+        if (pair_gemm && (rc = upload_packed_pair(w, 4 * C, C, BN, &L.wfc_p))) return rc;
         w += 4 * CC;
         const float *wproj2 = w;
         if ((rc = upload_packed(w, C, 4 * C, BN, &L.wproj2))) return rc;
+        if (pair_gemm && (rc = upload_packed_pair(w, C, 4 * C, BN, &L.wproj2_p))) return rc;
         w += 4 * CC;
         if (m.fused) {
             // the fused kernel of block l also computes block l+1's c_attn; its weights sit one block further in the buffer

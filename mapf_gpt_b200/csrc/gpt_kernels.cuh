@@ -19,6 +19,7 @@ enum { EPI_STORE_F32 = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_GELU = 3 };
 struct GemmArgs {
     const __nv_bfloat16 *A;  // A_ti
     const __nv_bfloat16 *W;  // W_ti packed for this BN
+    const __nv_bfloat16 *Wp; // the same weights packed for CTA pairs (gemm_pair_kernel), or nullptr
     void *out;               // see epilogues
     int M, N, K;             // M % 128 == 0, N % BN == 0, K % BK == 0
     int C, n_head, hs;       // EPI_QKV only
@@ -219,6 +220,189 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
     __syncthreads();
     if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem);
 }
+
+// ---------------------------------------------------------------------------------------------
+// The same GEMM on CTA PAIRS (cta_group::2): C[256 x BN] per pair = two adjacent 128-row tiles, ONE M = 256 UMMA per k-step
+// issued by the leader; A = each CTA's own rows, B = BN/2 weight rows from each CTA's ring.  Per CTA and k-block the ring
+// takes 128 x BK of A + BN/2 x BK of W instead of 128 x BK + BN x BK: at BN = 256 the L2 -> SM traffic per FLOP drops by a
+// third and a third stage fits (ncu, C = 768: the single-CTA kernel pulls 87-116 GB per launch through L2 -> SM and stalls
+// there).  Eight epilogue warps (two per TMEM lane quadrant, half of the columns each); the residual epilogue fetches x
+// one 32-column chunk ahead of the accumulator it is added to.  Protocol as post_attn_kernel<.., CL = 2>: the peer's UMMA
+// warp relays "my stage landed" to the leader, the leader's commits are multicast to both CTAs.
+// warps 0-7: epilogue, warp 8: bulk-copy producer, warp 9: UMMA issuer (leader) / relay (peer).
+// W is packed [N/BN][2 halves][K/8][BN/2][8] (upload_packed_pair).
+// ---------------------------------------------------------------------------------------------
+template <int BN, int BK, int STAGES, int EPI>
+__global__ void __launch_bounds__(320, 2) gemm_pair_kernel(const GemmArgs a)
+{
+    constexpr int A_BYTES = BK * 256;            // [BK/8][128][16 B]
+    constexpr int B_BYTES = BK * (BN / 2) * 2;   // [BK/8][BN/2][16 B]: this CTA's half of the weight rows
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr int HALF = BN / 2;                 // accumulator columns per epilogue warp
+    static_assert(BN % 64 == 0 && BN <= 256, "gemm_pair_kernel: BN in {64, 128, 192, 256}");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *pfull = empty + STAGES;            // leader only: the peer's stage landed (relayed)
+    uint64_t *acc_bar = pfull + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+    uint32_t *qkv_off = tmem_slot + 2;           // EPI_QKV: uint4 offset of each 8-column group inside a sequence's q/k/v block
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int NT = a.N / BN;
+    const int pair = blockIdx.x >> 1;
+    const int nt = pair % NT, mt = (pair / NT) * 2 + (int)crank;
+    const int KB = a.K / BK;
+    if constexpr (EPI == EPI_QKV) {
+        if (threadIdx.x < BN / 8) {
+            const int n = nt * BN + 8 * threadIdx.x;
+            const int which = n / a.C, rem = n - which * a.C;
+            const int head = rem / a.hs, d0 = rem - head * a.hs;
+            qkv_off[threadIdx.x] = (uint32_t)(((which * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256);
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&pfull[s], 1);
+        }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const __nv_bfloat16 *srcA = a.A + (size_t)mt * (a.K / 8) * 1024;
+            const __nv_bfloat16 *srcB = a.Wp + ((size_t)nt * 2 + crank) * (a.K / 8) * (HALF * 8);
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                uint8_t *st = smem + s * STAGE_BYTES;
+                bulk_g2s(st, srcA + (size_t)kb * (BK / 8) * 1024, A_BYTES, &full[s]);
+                bulk_g2s(st + A_BYTES, srcB + (size_t)kb * (BK / 8) * (HALF * 8), B_BYTES, &full[s]);
+            }
+        }
+    } else if (warp == 9 && !leader) {
+        for (int kb = 0; kb < KB; kb++) {   // relay: my half of stage kb has landed
+            const int s = kb % STAGES;
+            mbar_wait(&full[s], (kb / STAGES) & 1);
+            if (lane == 0) mbar_arrive_cluster(&pfull[s], 0);
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+        for (int kb = 0; kb < KB; kb++) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            mbar_wait(&pfull[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ks++)
+                    umma_ss_pair(tmem, umma_desc(sa + ks * 2 * 2048, 2048, 128), umma_desc(sb + ks * 2 * (HALF * 16), HALF * 16, 128),
+                                 idesc, (kb | ks) != 0 ? 1u : 0u);
+                umma_commit_pair(&empty[s], (uint16_t)3);   // frees the stage in both CTAs when these UMMAs retire
+                if (kb == KB - 1) umma_commit_pair(acc_bar, (uint16_t)3);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- epilogue: TMEM lane quadrant = warp & 3, column half = warp >> 2
+        const int q = warp & 3, hsel = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + hsel * HALF;
+        const int nbase = nt * BN + hsel * HALF;
+        if constexpr (EPI == EPI_RESID) {
+            float4 *X = reinterpret_cast<float4 *>(a.out) + ((size_t)mt * (a.N / 4) + nbase / 4) * 128 + r;
+            float4 xa[8], xb[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) xa[j] = X[(size_t)j * 128];          // first chunk: on its way while the UMMAs run
+            mbar_wait(acc_bar, 0);
+            tc_fence_after();
+            auto chunk = [&](int c0, float4 (&x)[8], float4 (&xn)[8]) {
+                if (c0 + 32 < HALF) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) xn[j] = X[(size_t)((c0 + 32) / 4 + j) * 128];
+                }
+                uint32_t v[32];
+                tmem_ld32(trow + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    x[j].x += __uint_as_float(v[4 * j + 0]);
+                    x[j].y += __uint_as_float(v[4 * j + 1]);
+                    x[j].z += __uint_as_float(v[4 * j + 2]);
+                    x[j].w += __uint_as_float(v[4 * j + 3]);
+                    X[(size_t)(c0 / 4 + j) * 128] = x[j];
+                }
+            };
+#pragma unroll 1
+            for (int c0 = 0; c0 < HALF; c0 += 64) {
+                chunk(c0, xa, xb);
+                chunk(c0 + 32, xb, xa);
+            }
+        } else {
+            mbar_wait(acc_bar, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < HALF; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c0, v);
+                tmem_wait_ld();
+                const int n0 = nbase + c0;
+                if constexpr (EPI == EPI_STORE_F32) {
+                    float *C = reinterpret_cast<float *>(a.out) + (size_t)(mt * 128 + r) * a.N + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) C[j] = __uint_as_float(v[j]);
+                } else if constexpr (EPI == EPI_GELU) {
+                    uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.N / 8) + n0 / 8) * 128 + r;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint4 o;
+                        o.x = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])));
+                        o.y = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])));
+                        o.z = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])));
+                        o.w = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                        O[(size_t)j * 128] = o;
+                    }
+                } else {  // EPI_QKV: scatter into [seq][3][head][hs/8][256][8]
+                    const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
+                    uint4 *Oseq = reinterpret_cast<uint4 *>(a.out) + (size_t)seq * (3 * a.C / 8) * 256 + tok;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                        Oseq[qkv_off[(hsel * HALF + c0) / 8 + j]] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();           // neither CTA leaves (or frees TMEM) while the pair's UMMAs / commits may still target it
+    if (warp == 9) tmem_dealloc_pair<TMEM_COLS>(tmem);
+}
+template <int BN, int BK, int STAGES>
+constexpr int gemm_pair_smem_bytes() { return STAGES * (BK * 256 + BK * (BN / 2) * 2) + (3 * STAGES + 1) * 8 + 16 + (BN / 8) * 4; }
 
 template <int BN, int BK, int STAGES>
 constexpr int gemm_smem_bytes() { return STAGES * (BK * 256 + BK * BN * 2) + (2 * STAGES + 1) * 8 + 16 + (BN / 8) * 4; }
@@ -1011,6 +1195,58 @@ __global__ void __launch_bounds__(128) ln_kernel(const float *__restrict__ X, co
         o.z = pack_bf16x2((v1.x - mean) * rstd * g1.x, (v1.y - mean) * rstd * g1.y);
         o.w = pack_bf16x2((v1.z - mean) * rstd * g1.z, (v1.w - mean) * rstd * g1.w);
         O[(size_t)c8 * 128] = o;
+    }
+}
+
+// Same LayerNorm with ONE pass over HBM (the kernel above reads every row three times: 19.3 GB instead of 6.4 GB per
+// 2 097 152 tokens at C = 768, ncu).  Block = 32 rows of a tile x 8 warps; warp w keeps NPW = C/32 float4 groups of its
+// lane's row in registers, mean and variance are two shared-memory reductions over the 8 warps (two-pass arithmetic, one
+// memory pass).  A warp-level access is 32 rows x 16 B = 512 contiguous bytes.
+template <int NPW>
+__global__ void __launch_bounds__(256, 2) ln_rows_kernel(const float *__restrict__ X, const float *__restrict__ gain,
+                                                      __nv_bfloat16 *__restrict__ out)
+{
+    constexpr int C = NPW * 32;
+    static_assert(NPW % 2 == 0, "a warp owns whole 8-column output groups");
+    __shared__ float red[2][8][32];
+    const int mt = blockIdx.x >> 2, r = ((blockIdx.x & 3) << 5) + (threadIdx.x & 31), w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 *Xi = reinterpret_cast<const float4 *>(X) + ((size_t)mt * (C / 4) + w * NPW) * 128 + r;
+    float4 v[NPW];
+#pragma unroll
+    for (int i = 0; i < NPW; i++) v[i] = Xi[(size_t)i * 128];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPW; i++) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    red[0][w][lane] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tot += red[0][k][lane];
+    const float mean = tot / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPW; i++) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    red[1][w][lane] = q;
+    __syncthreads();
+    float qt = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) qt += red[1][k][lane];
+    const float rstd = rsqrtf(qt / (float)C + 1e-5f);
+    uint4 *O = reinterpret_cast<uint4 *>(out) + ((size_t)mt * (C / 8) + w * (NPW / 2)) * 128 + r;
+    const float4 *g4 = reinterpret_cast<const float4 *>(gain) + w * NPW;
+#pragma unroll
+    for (int i = 0; i < NPW / 2; i++) {
+        const float4 v0 = v[2 * i], v1 = v[2 * i + 1];
+        const float4 g0 = __ldg(g4 + 2 * i), g1 = __ldg(g4 + 2 * i + 1);
+        uint4 o;
+        o.x = pack_bf16x2((v0.x - mean) * rstd * g0.x, (v0.y - mean) * rstd * g0.y);
+        o.y = pack_bf16x2((v0.z - mean) * rstd * g0.z, (v0.w - mean) * rstd * g0.w);
+        o.z = pack_bf16x2((v1.x - mean) * rstd * g1.x, (v1.y - mean) * rstd * g1.y);
+        o.w = pack_bf16x2((v1.z - mean) * rstd * g1.z, (v1.w - mean) * rstd * g1.w);
+        O[(size_t)i * 128] = o;
     }
 }
 
