@@ -333,9 +333,15 @@ static int launch_gemm_pair(mg_engine *e, const GemmArgs &a, int kc)
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
+    static const bool dbg = getenv("MAPF_GPT_B200_DEBUG_SYNC") != nullptr;   // hang hunt: name every launch, wait for it
+    if (dbg) fprintf(stderr, "gemm_pair EPI %d M %d N %d K %d ...", EPI, a.M, a.N, a.K);
     prof_begin(e, kc);
     CU(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN, BK, STAGES, EPI>, a));
     prof_end(e);
+    if (dbg) {
+        CU(cudaStreamSynchronize(e->stream));
+        fprintf(stderr, " done\n");
+    }
     CU(cudaGetLastError());
     return MG_OK;
 }
