@@ -315,7 +315,9 @@ template <int EPI>
 static int launch_gemm_pair(mg_engine *e, const GemmArgs &a, int kc)
 {
     constexpr int BN = 256, BK = 64, STAGES = 3;
-    constexpr int smem = gemm_pair_smem_bytes<BN, BK, STAGES>();
+    // MAPF_GPT_B200_GEMM_PAIR_1CTA=1 (hang hunt): pad the dynamic shared memory so that only ONE CTA fits per SM
+    static const bool one_cta = getenv("MAPF_GPT_B200_GEMM_PAIR_1CTA") != nullptr;
+    const int smem = one_cta ? 120 * 1024 : gemm_pair_smem_bytes<BN, BK, STAGES>();
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(gemm_pair_kernel<BN, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -490,10 +492,13 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         const int M = ns * 256, MT = M / 128;
         if (m.fused) {
             prof_begin(e, KC_EMBED);
+            // with >= 2 blocks the first post_attn takes its residual tile from the table itself: the lookup writes q/k/v only
+            static const bool x_via_hbm = getenv("MAPF_GPT_B200_BLOCK0_X_VIA_HBM") != nullptr;
+            const bool x_from_tab = m.tab0 && m.cfg.n_layer >= 2 && !x_via_hbm;
             if (m.tab0 && C == 160)
-                block0_lookup_kernel<160><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, w.X, w.QKV);
+                block0_lookup_kernel<160><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, x_from_tab ? nullptr : w.X, w.QKV);
             else if (m.tab0 && C == 256)
-                block0_lookup_kernel<256><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, w.X, w.QKV);
+                block0_lookup_kernel<256><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, x_from_tab ? nullptr : w.X, w.QKV);
             else
                 embed_ln_kernel<<<MT, 128, 67 * (C + 4) * 4, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe_ti, m.layers[0].ln1,
                                                                           w.X, w.XN, C);
@@ -536,6 +541,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 pa.qkv_out = (!last && m.fuse_qkv) ? w.QKV : nullptr;
                 pa.n_head = H; pa.hs = hs;
                 pa.timeline = e->d_timeline;
+                if (l == 0 && x_from_tab) { pa.tokens0 = tokens + (size_t)s0 * 256; pa.tab0 = m.tab0; pa.tab_nrec = C / 4 + 3 * C / 8; }
                 if ((rc = launch_post_attn(e, C, pa, MT, false))) return rc;
             }
             if (e->prune_last) continue;

@@ -35,6 +35,11 @@ struct PostAttnArgs {
     // follow the 18 regular ones in `wstream`.  nullptr = write xn_out instead.
     __nv_bfloat16 *qkv_out;        // [seq][3][head][hs/8][256][8]
     int n_head, hs;
+    // block 0 only: the residual tile comes straight from the (token, position) table (block0_lookup_kernel then writes q/k/v
+    // only: x never makes the HBM round trip).  nullptr = read a.x.
+    const uint8_t *tokens0;        // [MT * 128] token ids of this chunk
+    const uint4 *tab0;             // [67][256][tab_nrec] records, x first
+    int tab_nrec;
 };
 // steady-state CTAs (not the first wave, whose loads all hit DRAM at once); single-tile launches have fewer CTAs and stamp nothing
 #define MG_STAMP_CTA0 2048u
@@ -223,9 +228,17 @@ post_attn_kernel(const PostAttnArgs a)
     constexpr int HALF = C / 2;                           // residual columns handled by one worker thread
     float4 xv[HALF / 4];
     if (warp < 8 * NT) {
-        const float4 *Xl = reinterpret_cast<const float4 *>(a.x) + (size_t)(mt0 + (warp >> 3)) * (C / 4) * 128 + (warp & 3) * 32 + lane;
+        const int mtl = mt0 + (warp >> 3), row = (warp & 3) * 32 + lane, hh = (warp >> 2) & 1;
+        if (a.tab0 != nullptr) {   // block 0: this thread's 2C contiguous bytes of its token's record (L2-resident table)
+            const int tok = min((int)a.tokens0[(size_t)mtl * 128 + row], 66);
+            const float4 *src = reinterpret_cast<const float4 *>(a.tab0 + ((size_t)tok * 256 + ((mtl & 1) << 7) + row) * a.tab_nrec) + hh * (HALF / 4);
 #pragma unroll
-        for (int j = 0; j < HALF / 4; j++) xv[j] = Xl[(size_t)(((warp >> 2) & 1) * (HALF / 4) + j) * 128];
+            for (int j = 0; j < HALF / 4; j++) xv[j] = __ldg(src + j);
+        } else {
+            const float4 *Xl = reinterpret_cast<const float4 *>(a.x) + (size_t)mtl * (C / 4) * 128 + row;
+#pragma unroll
+            for (int j = 0; j < HALF / 4; j++) xv[j] = Xl[(size_t)(hh * (HALF / 4) + j) * 128];
+        }
     }
     if (threadIdx.x == 0) {
         mbar_init(bar_proj, 1);
@@ -782,7 +795,7 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) { *p = v; }
 // memory (row pitch CH + 1 groups: conflict-free 16-byte accesses), and written token-major (512 contiguous bytes per warp).
 template <int C>
 __global__ void __launch_bounds__(128) block0_lookup_kernel(const uint8_t *__restrict__ tokens, const uint4 *__restrict__ tab,
-                                                            float *__restrict__ X, __nv_bfloat16 *__restrict__ QKV)
+                                                            float *__restrict__ X, __nv_bfloat16 *__restrict__ QKV)   // X == nullptr: q/k/v only
 {
     constexpr int NX = C / 4, NQ = 3 * C / 8, NREC = NX + NQ;
     constexpr int CH = C == 160 ? 10 : 8, PITCH = CH + 1;       // groups per pass; NX and NQ are multiples of CH
@@ -796,7 +809,7 @@ __global__ void __launch_bounds__(128) block0_lookup_kernel(const uint8_t *__res
     uint4 *Q4 = reinterpret_cast<uint4 *>(QKV) + (size_t)seq * NQ * 256 + t;
     __syncthreads();
 #pragma unroll 1
-    for (int g0 = 0; g0 < NREC; g0 += CH) {
+    for (int g0 = X != nullptr ? 0 : NX; g0 < NREC; g0 += CH) {
         uint4 v[CH];
 #pragma unroll
         for (int k = 0; k < CH; k++) {
@@ -887,26 +900,46 @@ __global__ void __launch_bounds__(512) last_attn_kernel(const __nv_bfloat16 *__r
 #pragma unroll
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
-    // o[d] = sum_j p_j v[j][d]: lane owns d = lane (+32 for hs 64); p_j broadcast from its owner lane
-    float o0 = 0.f, o1 = 0.f;
+    // o[d] = sum_j p_j v[j][d]: every lane accumulates all HS dims over ITS OWN 8 keys from 16-byte V loads (a warp-level load
+    // is 512 contiguous bytes), then the 32 partial vectors are summed across the warp by a transposing butterfly: after step
+    // k a lane holds HS >> k dims, after five steps lane l holds dims {l} (hs 32) or {2l, 2l+1} (hs 64) summed over all keys.
+    float o[HS];
+#pragma unroll
+    for (int d = 0; d < HS; d++) o[d] = 0.f;
+    const uint4 *Vg4 = reinterpret_cast<const uint4 *>(Vg);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-#pragma unroll 8
-        for (int l = 0; l < 32; l++) {
-            const float p = __shfl_sync(0xffffffffu, s[i], l);
-            const int key = l + 32 * i;
-            o0 = fmaf(p, __bfloat162float(Vg[((size_t)(lane >> 3) * 256 + key) * 8 + (lane & 7)]), o0);
-            if (HS == 64) o1 = fmaf(p, __bfloat162float(Vg[((size_t)((lane + 32) >> 3) * 256 + key) * 8 + (lane & 7)]), o1);
+        const int key = lane + 32 * i;
+#pragma unroll
+        for (int c = 0; c < HS / 8; c++) {
+            const uint4 u = Vg4[(size_t)c * 256 + key];
+            const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                o[8 * c + 2 * j] = fmaf(s[i], f.x, o[8 * c + 2 * j]);
+                o[8 * c + 2 * j + 1] = fmaf(s[i], f.y, o[8 * c + 2 * j + 1]);
+            }
         }
     }
-    __nv_bfloat16 *dst = att_c + (size_t)mtc * C * 128;
-    {
-        const int col = head * HS + lane;
-        dst[((size_t)(col >> 3) * 128 + rc) * 8 + (col & 7)] = __float2bfloat16(o0 * inv);
-        if (HS == 64) {
-            const int col1 = col + 32;
-            dst[((size_t)(col1 >> 3) * 128 + rc) * 8 + (col1 & 7)] = __float2bfloat16(o1 * inv);
+    // butterfly: at step `off` a lane keeps the half of its dims selected by bit `off` of its lane id and adds the partner's
+#pragma unroll
+    for (int off = 16, n = HS; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int d = 0; d < n / 2; d++) {
+            const float keep = up ? o[d + n / 2] : o[d];
+            const float give = up ? o[d] : o[d + n / 2];
+            o[d] = keep + __shfl_xor_sync(0xffffffffu, give, off);
         }
+    }
+    // bit 4 of the lane id chose the top half first, bit 0 the last: the lane owns dims [lane * HS/32, (lane + 1) * HS/32)
+    __nv_bfloat16 *dst = att_c + (size_t)mtc * C * 128;
+    const int base = lane * (HS / 32);
+#pragma unroll
+    for (int k = 0; k < HS / 32; k++) {
+        const int col = head * HS + base + k;
+        dst[((size_t)(col >> 3) * 128 + rc) * 8 + (col & 7)] = __float2bfloat16(o[k] * inv);
     }
 }
 
