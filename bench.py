@@ -267,7 +267,8 @@ def main():
                   "post_attn_fused": 2 * 9 * C * C}   # per token
         if fuse_qkv:
             kflops["post_attn_fused"] += 2 * 3 * C * C       # + the next block's c_attn
-        kbytes = {"block0_lookup": 10 * C, "embed": 6 * C, "attention_last_token": 4 * C}
+        x_from_tab = table0 and cfg.n_layer >= 2 and os.environ.get("MAPF_GPT_B200_BLOCK0_X_VIA_HBM") is None
+        kbytes = {"block0_lookup": (6 if x_from_tab else 10) * C, "embed": 6 * C, "attention_last_token": 4 * C}
         kern = {}
         if table0 and "embed" in ktimes:       # block 0 runs as the (token, position) lookup, not embedding + LN + GEMM
             ktimes = {("block0_lookup" if k == "embed" else k): v for k, v in ktimes.items()}
