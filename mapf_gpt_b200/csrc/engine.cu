@@ -417,19 +417,6 @@ static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cu
         }
         aa.work_counter = ctr;
     }
-    static const bool wide = getenv("MAPF_GPT_B200_ATTN_WIDE") != nullptr;   // experiment: one 16-warp CTA per SM (measured slower: 1.06 vs 1.01 ms)
-    if (wide) {
-        static bool wide_attr = false;
-        if (!wide_attr) {
-            CU(cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_wide_smem_bytes()));
-            wide_attr = true;
-        }
-        if (e) prof_begin(e, KC_ATTN);
-        attn_wide_kernel<<<std::min(n_items, n_sms), 576, attn_wide_smem_bytes(), st>>>(aa, n_items);
-        if (e) prof_end(e);
-        CU(cudaGetLastError());
-        return MG_OK;
-    }
     if (e) prof_begin(e, KC_ATTN);
     attn_persistent_kernel<<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(aa, n_items);
     if (e) prof_end(e);

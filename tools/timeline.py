@@ -18,7 +18,7 @@ print("kernel times of this single forward (cold clocks, no sustained power cap)
 eng.set_profiling(False)
 out = np.zeros((17, 128), np.int64)
 L.mg_test_timeline(eng._h, 0, out.ctypes.data_as(C.c_void_p))
-names = {0: "mma:start", 1: "mma:att ready", 2: "mma:proj issued", 3: "mma:FC(0) stage landed", 4: "mma:ln2 seen", 5: "prod:refill S issued", 6: "prod:refill S+1 issued", 40: "mma:all issued",
+names = {0: "mma:start", 1: "mma:att ready", 2: "mma:proj issued", 40: "mma:all issued",
          50: "wrk:proj done", 51: "wrk:epi1 pass1", 52: "wrk:ln2 arrive", 90: "wrk:done seen", 91: "wrk:end"}
 names.update({100: "att:start", 101: "att:QK landed", 102: "att:P+V ready", 103: "att:PV issued", 110: "att:S seen",
               111: "att:max done", 112: "att:P arrive", 113: "att:O seen", 114: "att:end"})
@@ -29,9 +29,6 @@ if "--classic-attn" not in sys.argv:   # persistent attention kernel: item 40 of
         names.update({100 + 3 * qt: f"att{qt}:mma S issue", 101 + 3 * qt: f"att{qt}:mma P ready", 102 + 3 * qt: f"att{qt}:mma PV issued",
                       110 + 8 * qt: f"att{qt}:wrk S seen", 111 + 8 * qt: f"att{qt}:wrk max done", 112 + 8 * qt: f"att{qt}:wrk max exchanged",
                       113 + 8 * qt: f"att{qt}:wrk P arrive", 114 + 8 * qt: f"att{qt}:wrk O seen", 115 + 8 * qt: f"att{qt}:wrk end"})
-        if "--narrow-attn" not in sys.argv:   # attn_wide_kernel: ids 113-115 mean something else
-            names.update({113 + 8 * qt: f"att{qt}:wrk O(prev) drained", 114 + 8 * qt: f"att{qt}:wrk P arrive", 115 + 8 * qt: f"att{qt}:wrk O(prev) stored",
-                          101 + 3 * qt: f"att{qt}:mma P ready", 102 + 3 * qt: f"att{qt}:mma PV issued"})
 names.update({92: "wrk:x' stored", 93: "wrk:qa arrive (LN1_next in smem)"})
 names.update({94 + hh: f"wrk:qkv half-tile {hh} seen" for hh in range(6)})
 names.update({126: "att:CTA start", 127: "att:CTA end"})
