@@ -113,3 +113,13 @@ def test_bench_flops_formula():
     assert bench.flops_per_agent_step(5, 160) == 996_168_640
     assert bench.flops_per_agent_step(8, 256) == 3_758_130_688
     assert bench.flops_per_agent_step(12, 768) == 45_902_565_888
+
+
+def test_cost2go_cache_golden_is_self_consistent():
+    """precomputed_cost2go.bin (cpp:114-131): size_t rows, size_t cols, rows x cols uint16 -- the golden record written by
+    tests/golden/make_cache_golden.py from the unmodified reference must describe exactly that layout."""
+    import json
+    g = json.loads((Path(__file__).parent / "golden" / "cost2go_cache_golden.json").read_text())
+    assert g["rows"] == g["cols"] > 0
+    assert g["bytes"] == 16 + 2 * g["rows"] * g["cols"]
+    assert len(g["sha256"]) == 64
