@@ -311,10 +311,10 @@ static int launch_gemm_cfg(mg_engine *e, const GemmArgs &a, int kc)
     CU(cudaGetLastError());
     return MG_OK;
 }
-template <int EPI>
+template <int EPI, int BN>
 static int launch_gemm_pair(mg_engine *e, const GemmArgs &a, int kc)
 {
-    constexpr int BN = 256, BK = 64, STAGES = 3;
+    constexpr int BK = 64, STAGES = BN == 256 ? 3 : 4;
     // MAPF_GPT_B200_GEMM_PAIR_1CTA=1 (hang hunt): pad the dynamic shared memory so that only ONE CTA fits per SM
     static const bool one_cta = getenv("MAPF_GPT_B200_GEMM_PAIR_1CTA") != nullptr;
     const int smem = one_cta ? 120 * 1024 : gemm_pair_smem_bytes<BN, BK, STAGES>();
@@ -355,7 +355,8 @@ static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
     // of six processes hung in their first forward on the GPU box (two CTA pairs co-resident per SM pair, 147k short-lived CTAs per
     // launch; suspected tcgen05.alloc.cta_group::2 permit inversion).  Not shipped as a default until that is understood.
     static const bool pair_on = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
-    if (e && a.Wp && pair_on && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI>(e, a, kc);
+    if (e && a.Wp && pair_on && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI, 256>(e, a, kc);
+    if (e && a.Wp && pair_on && BN == 128 && a.N % 128 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI, 128>(e, a, kc);
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
     if (BN == 256 && a.N % 256 == 0 && a.K % 64 == 0) return launch_gemm_cfg<256, 64, 2, EPI>(e, a, kc);
@@ -368,6 +369,7 @@ static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 }
 static int pick_bn(int C)
 {
+    if (C % 128 == 0 && getenv("MAPF_GPT_B200_BN128") != nullptr) return 128;   // hang hunt / A-B of the generic GEMM tile width
     if (C % 256 == 0) return 256;
     if (C % 160 == 0) return 160;
     if (C % 128 == 0) return 128;
@@ -972,7 +974,7 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         const char *np = getenv("MAPF_GPT_B200_NO_PRUNE");
         e->prune_last = !(np && np[0] == '1');
     }
-    const bool pair_gemm = !m.fused && BN == 256 && getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
+    const bool pair_gemm = !m.fused && (BN == 256 || BN == 128) && getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;
