@@ -347,14 +347,54 @@ static int launch_gemm_pair(mg_engine *e, const GemmArgs &a, int kc)
     CU(cudaGetLastError());
     return MG_OK;
 }
+// persistent CTA-pair GEMM (gemm_pair_persistent_kernel): one pair per SM pair, two TMEM accumulators
+template <int EPI>
+static int launch_gemm_pair_persistent(mg_engine *e, const GemmArgs &a, int kc)
+{
+    constexpr int BN = 256, BK = 64, STAGES = 6;
+    const int smem = gemm_pair_persistent_smem_bytes<BN, BK, STAGES>(a.N);
+    constexpr int SMEM_MAX = 224 * 1024;
+    if (smem > SMEM_MAX) return fail(MG_ERR_ARG, "gemm: N=%d too wide for the persistent pair kernel", a.N);
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (!max_clusters) {
+        CU(cudaFuncSetAttribute(gemm_pair_persistent_kernel<BN, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        cfg.gridDim = dim3(2 * 74);
+        int n = 0;
+        CU(cudaOccupancyMaxActiveClusters(&n, gemm_pair_persistent_kernel<BN, BK, STAGES, EPI>, &cfg));
+        max_clusters = n > 0 ? n : 1;
+    }
+    const int n_tiles = (a.M / 256) * (a.N / BN);
+    cfg.gridDim = dim3(2 * std::min(max_clusters, n_tiles));
+    prof_begin(e, kc);
+    CU(cudaLaunchKernelEx(&cfg, gemm_pair_persistent_kernel<BN, BK, STAGES, EPI>, a));
+    prof_end(e);
+    CU(cudaGetLastError());
+    return MG_OK;
+}
 template <int EPI>
 static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 {
     if (a.M % 128) return fail(MG_ERR_ARG, "gemm: M=%d not a multiple of 128", a.M);
-    // CTA pairs (cta_group::2, gemm_pair_kernel) are OPT-IN (MAPF_GPT_B200_GEMM_PAIR=1): +6 % on the 85M step, parity-green, but two
-    // of six processes hung in their first forward on the GPU box (two CTA pairs co-resident per SM pair, 147k short-lived CTAs per
-    // launch; suspected tcgen05.alloc.cta_group::2 permit inversion).  Not shipped as a default until that is understood.
-    static const bool pair_on = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
+    // MAPF_GPT_B200_GEMM_PAIR: 2 (default) = persistent CTA pairs, one pair per SM pair, two TMEM accumulators (+18 % on the 85M step);
+    // 0 = the single-CTA kernel; 1 = the non-persistent pair kernel, an experiment kept for the record: with two pairs co-resident per
+    // SM pair its first c_fc launch of a process hung intermittently on a warmed-up GPU.
+    const char *pair_env = getenv("MAPF_GPT_B200_GEMM_PAIR");
+    static const int pair_mode = pair_env ? atoi(pair_env) : 2;
+    static const bool pair_on = pair_mode == 1;
+    static const bool pair_persistent = pair_mode == 2;
+    if (e && a.Wp && pair_persistent && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
+        return launch_gemm_pair_persistent<EPI>(e, a, kc);
     if (e && a.Wp && pair_on && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI, 256>(e, a, kc);
     if (e && a.Wp && pair_on && BN == 128 && a.N % 128 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI, 128>(e, a, kc);
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
@@ -974,7 +1014,8 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         const char *np = getenv("MAPF_GPT_B200_NO_PRUNE");
         e->prune_last = !(np && np[0] == '1');
     }
-    const bool pair_gemm = !m.fused && (BN == 256 || BN == 128) && getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '1';
+    const char *pair_env = getenv("MAPF_GPT_B200_GEMM_PAIR");
+    const bool pair_gemm = !m.fused && (BN == 256 || BN == 128) && (pair_env ? atoi(pair_env) : 2) != 0;
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;

@@ -221,6 +221,88 @@ __global__ void __launch_bounds__(192) gemm_kernel(const GemmArgs a)
     if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+// Epilogue of one 128 x BN accumulator tile of a CTA-pair GEMM, run by 8 warps: TMEM lane quadrant = warp & 3, column half =
+// warp >> 2.  wait_acc() blocks until the accumulator is complete; drained() is called once the thread's last tcgen05.ld has
+// landed in registers (the persistent kernel hands the TMEM buffer back to the UMMA issuer there).
+template <int BN, int EPI, typename WaitAcc, typename Drained>
+__device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt, uint32_t tmem_acc, int warp, int lane,
+                                              const uint32_t *qkv_off, WaitAcc &&wait_acc, Drained &&drained)
+{
+    constexpr int HALF = BN / 2;
+    const int q = warp & 3, hsel = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16) + hsel * HALF;
+    const int nbase = nt * BN + hsel * HALF;
+    if constexpr (EPI == EPI_RESID) {
+        float4 *X = reinterpret_cast<float4 *>(a.out) + ((size_t)mt * (a.N / 4) + nbase / 4) * 128 + r;
+        float4 xa[8], xb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) xa[j] = X[(size_t)j * 128];          // first chunk: on its way while the UMMAs run
+        wait_acc();
+        auto chunk = [&](int c0, float4 (&x)[8], float4 (&xn)[8]) {
+            if (c0 + 32 < HALF) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) xn[j] = X[(size_t)((c0 + 32) / 4 + j) * 128];
+            }
+            uint32_t v[32];
+            tmem_ld32(trow + c0, v);
+            tmem_wait_ld();
+            if (c0 + 32 >= HALF) drained();
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                x[j].x += __uint_as_float(v[4 * j + 0]);
+                x[j].y += __uint_as_float(v[4 * j + 1]);
+                x[j].z += __uint_as_float(v[4 * j + 2]);
+                x[j].w += __uint_as_float(v[4 * j + 3]);
+                X[(size_t)(c0 / 4 + j) * 128] = x[j];
+            }
+        };
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF; c0 += 64) {
+            chunk(c0, xa, xb);
+            chunk(c0 + 32, xb, xa);
+        }
+    } else {
+        wait_acc();
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(trow + c0, v);
+            tmem_wait_ld();
+            if (c0 + 32 >= HALF) drained();
+            const int n0 = nbase + c0;
+            if constexpr (EPI == EPI_STORE_F32) {
+                float *C = reinterpret_cast<float *>(a.out) + (size_t)(mt * 128 + r) * a.N + n0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) C[j] = __uint_as_float(v[j]);
+            } else if constexpr (EPI == EPI_GELU) {
+                uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.N / 8) + n0 / 8) * 128 + r;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 o;
+                    o.x = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])));
+                    o.y = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])));
+                    o.z = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])));
+                    o.w = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    O[(size_t)j * 128] = o;
+                }
+            } else {  // EPI_QKV: scatter into [seq][3][head][hs/8][256][8]
+                const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
+                uint4 *Oseq = reinterpret_cast<uint4 *>(a.out) + (size_t)seq * (3 * a.C / 8) * 256 + tok;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                    o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                    o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                    o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                    Oseq[qkv_off[(hsel * HALF + c0) / 8 + j]] = o;
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The same GEMM on CTA PAIRS (cta_group::2): C[256 x BN] per pair = two adjacent 128-row tiles, ONE M = 256 UMMA per k-step
 // issued by the leader; A = each CTA's own rows, B = BN/2 weight rows from each CTA's ring.  Per CTA and k-block the ring
@@ -323,84 +405,148 @@ __global__ void __launch_bounds__(320, 2) gemm_pair_kernel(const GemmArgs a)
         }
     } else {
         // ---- epilogue: TMEM lane quadrant = warp & 3, column half = warp >> 2
-        const int q = warp & 3, hsel = warp >> 2;
-        const int r = q * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + hsel * HALF;
-        const int nbase = nt * BN + hsel * HALF;
-        if constexpr (EPI == EPI_RESID) {
-            float4 *X = reinterpret_cast<float4 *>(a.out) + ((size_t)mt * (a.N / 4) + nbase / 4) * 128 + r;
-            float4 xa[8], xb[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) xa[j] = X[(size_t)j * 128];          // first chunk: on its way while the UMMAs run
-            mbar_wait(acc_bar, 0);
-            tc_fence_after();
-            auto chunk = [&](int c0, float4 (&x)[8], float4 (&xn)[8]) {
-                if (c0 + 32 < HALF) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) xn[j] = X[(size_t)((c0 + 32) / 4 + j) * 128];
-                }
-                uint32_t v[32];
-                tmem_ld32(trow + c0, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    x[j].x += __uint_as_float(v[4 * j + 0]);
-                    x[j].y += __uint_as_float(v[4 * j + 1]);
-                    x[j].z += __uint_as_float(v[4 * j + 2]);
-                    x[j].w += __uint_as_float(v[4 * j + 3]);
-                    X[(size_t)(c0 / 4 + j) * 128] = x[j];
-                }
-            };
-#pragma unroll 1
-            for (int c0 = 0; c0 < HALF; c0 += 64) {
-                chunk(c0, xa, xb);
-                chunk(c0 + 32, xb, xa);
-            }
-        } else {
-            mbar_wait(acc_bar, 0);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < HALF; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(trow + c0, v);
-                tmem_wait_ld();
-                const int n0 = nbase + c0;
-                if constexpr (EPI == EPI_STORE_F32) {
-                    float *C = reinterpret_cast<float *>(a.out) + (size_t)(mt * 128 + r) * a.N + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) C[j] = __uint_as_float(v[j]);
-                } else if constexpr (EPI == EPI_GELU) {
-                    uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.N / 8) + n0 / 8) * 128 + r;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint4 o;
-                        o.x = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])));
-                        o.y = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])));
-                        o.z = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])));
-                        o.w = pack_bf16x2_p(gelu2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-                        O[(size_t)j * 128] = o;
-                    }
-                } else {  // EPI_QKV: scatter into [seq][3][head][hs/8][256][8]
-                    const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
-                    uint4 *Oseq = reinterpret_cast<uint4 *>(a.out) + (size_t)seq * (3 * a.C / 8) * 256 + tok;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                        Oseq[qkv_off[(hsel * HALF + c0) / 8 + j]] = o;
-                    }
-                }
-            }
-        }
+        pair_epilogue<BN, EPI>(a, mt, nt, tmem, warp, lane, qkv_off, [&]() { mbar_wait(acc_bar, 0); tc_fence_after(); }, []() {});
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();           // neither CTA leaves (or frees TMEM) while the pair's UMMAs / commits may still target it
     if (warp == 9) tmem_dealloc_pair<TMEM_COLS>(tmem);
 }
+// ---------------------------------------------------------------------------------------------
+// Persistent form: ONE CTA pair per SM pair (1 CTA per SM, the whole shared memory as a STAGES-deep ring), looping over
+// 256 x BN output tiles (n-tiles of the same 256 rows first, so concurrently running pairs share A in L2), TWO accumulator
+// buffers in TMEM (2 x BN columns): the 8 epilogue warps of both CTAs drain buffer b while the leader's UMMAs fill buffer b ^ 1.
+// No two pairs ever share an SM pair (the non-persistent kernel above hung intermittently with two co-resident pairs issuing
+// M = 256, N = 256 UMMAs).  Barriers on top of the ring: acc_full[2] (multicast commit) and, on the leader,
+// acc_empty[2] (one elected arrive per epilogue warp of both CTAs = 16).
+// ---------------------------------------------------------------------------------------------
+template <int BN, int BK, int STAGES, int EPI>
+__global__ void __launch_bounds__(320, 1) gemm_pair_persistent_kernel(const GemmArgs a)
+{
+    constexpr int A_BYTES = BK * 256, B_BYTES = BK * (BN / 2) * 2, STAGE_BYTES = A_BYTES + B_BYTES, HALF = BN / 2;
+    static_assert(BN == 256, "two accumulators of BN columns fill the 512 TMEM columns");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *pfull = empty + STAGES;
+    uint64_t *acc_full = pfull + STAGES;         // [2]
+    uint64_t *acc_empty = acc_full + 2;          // [2] (leader's copy is the one that counts)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint32_t *qkv_off = tmem_slot + 2;           // EPI_QKV: [3C/8] uint4 offsets of ALL 8-column groups (n-tiles change per tile)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int NT = a.N / BN, KB = a.K / BK;
+    const int n_tiles = (a.M / 256) * NT, pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if constexpr (EPI == EPI_QKV) {
+        for (int i = threadIdx.x; i < a.N / 8; i += blockDim.x) {
+            const int n = 8 * i;
+            const int which = n / a.C, rem = n - which * a.C;
+            const int head = rem / a.hs, d0 = rem - head * a.hs;
+            qkv_off[i] = (uint32_t)(((which * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256);
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&pfull[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 16);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc_pair<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int nt = tile % NT, mt = (tile / NT) * 2 + (int)crank;
+                const __nv_bfloat16 *srcA = a.A + (size_t)mt * (a.K / 8) * 1024;
+                const __nv_bfloat16 *srcB = a.Wp + ((size_t)nt * 2 + crank) * (a.K / 8) * (HALF * 8);
+                for (int kb = 0; kb < KB; kb++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    uint8_t *st = smem + s * STAGE_BYTES;
+                    bulk_g2s(st, srcA + (size_t)kb * (BK / 8) * 1024, A_BYTES, &full[s]);
+                    bulk_g2s(st + A_BYTES, srcB + (size_t)kb * (BK / 8) * (HALF * 8), B_BYTES, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 9 && !leader) {
+        int it = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs)
+            for (int kb = 0; kb < KB; kb++, it++) {   // relay: my half of this stage has landed
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                if (lane == 0) mbar_arrive_cluster(&pfull[s], 0);
+                __syncwarp();
+            }
+    } else if (warp == 9) {
+        constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+        int it = 0, k = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, k++) {
+            const int b = k & 1;
+            mbar_wait(&acc_empty[b], ((k >> 1) & 1) ^ 1);      // both CTAs' epilogue warps have drained buffer b
+            tc_fence_after();
+            for (int kb = 0; kb < KB; kb++, it++) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                mbar_wait(&pfull[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ks++)
+                        umma_ss_pair(tmem + b * BN, umma_desc(sa + ks * 2 * 2048, 2048, 128),
+                                     umma_desc(sb + ks * 2 * (HALF * 16), HALF * 16, 128), idesc, (kb | ks) != 0 ? 1u : 0u);
+                    umma_commit_pair(&empty[s], (uint16_t)3);
+                    if (kb == KB - 1) umma_commit_pair(&acc_full[b], (uint16_t)3);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        int k = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, k++) {
+            const int nt = tile % NT, mt = (tile / NT) * 2 + (int)crank, b = k & 1;
+            pair_epilogue<BN, EPI>(
+                a, mt, nt, tmem + b * BN, warp, lane, qkv_off + nt * (BN / 8),
+                [&]() {
+                    mbar_wait(&acc_full[b], (k >> 1) & 1);
+                    tc_fence_after();
+                },
+                [&]() {   // this thread's part of buffer b is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (leader) mbar_arrive(&acc_empty[b]);
+                        else mbar_arrive_cluster(&acc_empty[b], 0);
+                    }
+                    __syncwarp();
+                });
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 9) tmem_dealloc_pair<512>(tmem);
+}
+template <int BN, int BK, int STAGES>
+constexpr int gemm_pair_persistent_smem_bytes(int N) { return STAGES * (BK * 256 + BK * (BN / 2) * 2) + (3 * STAGES + 4) * 8 + 16 + (N / 8) * 4; }
+
 template <int BN, int BK, int STAGES>
 constexpr int gemm_pair_smem_bytes() { return STAGES * (BK * 256 + BK * (BN / 2) * 2) + (3 * STAGES + 1) * 8 + 16 + (BN / 8) * 4; }
 
