@@ -256,8 +256,10 @@ def main():
     if rank == 0:
         pk = peaks()
         F = flops_per_agent_step(cfg.n_layer, cfg.n_embd)
-        pruned = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1"
-        fuse_qkv = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
+        pruned = (cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_GENERIC", "0")[:1] != "1"
+                  and os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1")
+        fused_path = cfg.n_embd in (160, 256) and os.environ.get("MAPF_GPT_B200_GENERIC", "0")[:1] != "1"
+        fuse_qkv = fused_path and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
         table0 = fuse_qkv and os.environ.get("MAPF_GPT_B200_NO_BLOCK0_TABLE") is None
         Fx = flops_executed(cfg.n_layer, cfg.n_embd, pruned=pruned, block0_table=table0)
         C, L, T = cfg.n_embd, cfg.n_layer, 256
