@@ -76,6 +76,17 @@ def test_live_reference_small_maps(built):
         assert _rollout_pair(ref, grid, n, 25, 5, change_goals=True) == 0
 
 
+def test_live_reference_baseline_maps(built):
+    """The other BASELINE.json map families at their agent counts (warehouse 192, a Berlin tile 256, a puzzle at 4), goals changing
+    on the way: the C restatement against the unmodified reference, every token of every agent."""
+    ref = oracle.load_ref_module()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    for name, n, steps in [("wfi_warehouse", 192, 12), ("Berlin_1_256_07", 256, 10), ("puzzle-11", 4, 30)]:
+        grid = maps.load_map(name, solid_padding=False)["grid"]
+        assert _rollout_pair(ref, grid, n, steps, 3, change_goals=True) == 0, name
+
+
 def test_live_reference_large_map_windows(built):
     """> 128 cells: the windowed multi-source BFS (cpp:200-286) and the recompute trigger."""
     ref = oracle.load_ref_module()
