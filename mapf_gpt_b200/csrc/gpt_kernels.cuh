@@ -1051,6 +1051,8 @@ __global__ void __launch_bounds__(128) embed_kernel(const uint8_t *__restrict__ 
     const float4 *te = reinterpret_cast<const float4 *>(wte + (size_t)tok * C);
     const float4 *pe = reinterpret_cast<const float4 *>(wpe + (size_t)pos * C);
     float4 *Xo = reinterpret_cast<float4 *>(X) + (size_t)mt * (C / 4) * 128 + r;
+    // every lane walks its own two rows (16-byte reads that share L1 lines from one iteration to the next): keep 16 loads in flight
+#pragma unroll 8
     for (int c4 = 0; c4 < C / 4; c4++) {
         const float4 t = __ldg(te + c4), p = __ldg(pe + c4);
         Xo[(size_t)c4 * 128] = make_float4(t.x + p.x, t.y + p.y, t.z + p.z, t.w + p.w);
