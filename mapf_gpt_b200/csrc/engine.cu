@@ -470,6 +470,19 @@ static int launch_attn(mg_engine *e, const AttnArgs &a, int hs, int n_seq, cudaS
     static const bool classic = getenv("MAPF_GPT_B200_ATTN_CLASSIC") != nullptr;
     if (hs == 32 && !classic) return launch_attn_persistent(e, a, n_seq, st);
     if (hs == 32) return launch_attn_hs<32>(e, a, n_seq, st);
+    if (hs == 64 && !classic) {   // probabilities in TMEM, two CTAs per SM (attn_ts_kernel)
+        constexpr int smem = attn_ts_smem_bytes<64>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(attn_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        if (e) prof_begin(e, KC_ATTN);
+        attn_ts_kernel<64><<<n_seq * a.n_head, 288, smem, st>>>(a);
+        if (e) prof_end(e);
+        CU(cudaGetLastError());
+        return MG_OK;
+    }
     if (hs == 64) return launch_attn_hs<64>(e, a, n_seq, st);
     return fail(MG_ERR_ARG, "attention: head size %d unsupported (32 or 64)", hs);
 }

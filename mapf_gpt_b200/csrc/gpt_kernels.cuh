@@ -803,6 +803,189 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
 }
 
 // ---------------------------------------------------------------------------------------------
+// attn_ts_kernel<HS> (head size 64): the kernel above with the probabilities kept in TENSOR MEMORY (each thread converts its
+// half row of S in place to bf16 pairs, the P V UMMA takes A from TMEM) and the row sums accumulated by the threads instead
+// of by 16 extra ones-columns of V.  Without the 64 KB P tile and the ones block the CTA needs 80 KB of shared memory, so TWO
+// CTAs share an SM and one's softmax overlaps the other's loads and UMMAs (the smem-P kernel runs one CTA per SM at 17 %
+// tensor-pipe activity, profiles/r01e_85m_ncu.md).
+// TMEM (256 columns): S = [0,256); P (bf16x2) = [0,64) for keys 0..127 and [128,192) for keys 128..255; O = [64,64+HS).
+// ---------------------------------------------------------------------------------------------
+template <int HS>
+__global__ void __launch_bounds__(288, 2) attn_ts_kernel(const AttnArgs a)
+{
+    static_assert(HS == 64, "O = [64, 64 + HS) must fit between the two P ranges");
+    constexpr int Q_BYTES = 128 * HS * 2, K_BYTES = 256 * HS * 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *Qs = smem, *Ks = Qs + Q_BYTES, *Vs = Ks + K_BYTES;
+    float *redm = reinterpret_cast<float *>(Vs + K_BYTES);            // [2][128] row-max exchange
+    float *reds = redm + 256;                                         // [2][128] row-sum exchange
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reds + 256);
+    uint64_t *bK = bars, *bQ1 = bars + 1, *bV = bars + 2, *bS = bars + 3, *bP = bars + 4, *bO = bars + 5, *bE = bars + 6;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.x % a.n_head;
+    const int seq = blockIdx.x / a.n_head;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bK, 1);
+        mbar_init(bQ1, 1);
+        mbar_init(bV, 1);
+        mbar_init(bS, 1);
+        mbar_init(bP, 256);
+        mbar_init(bO, 1);
+        mbar_init(bE, 256);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // the whole warp runs the control flow (uniform-register descriptors), one elected lane issues
+        const size_t blk = (size_t)(HS / 8) * 256 * 8;  // elements per (seq, which, head)
+        const __nv_bfloat16 *Qg = a.qkv + (((size_t)seq * 3 + 0) * a.n_head + head) * blk;
+        const __nv_bfloat16 *Kg = a.qkv + (((size_t)seq * 3 + 1) * a.n_head + head) * blk;
+        const __nv_bfloat16 *Vg = a.qkv + (((size_t)seq * 3 + 2) * a.n_head + head) * blk;
+        if (lane == 0) {
+            mbar_expect_tx(bK, Q_BYTES + K_BYTES);
+#pragma unroll
+            for (int c = 0; c < HS / 8; c++) bulk_g2s(Qs + c * 2048, Qg + ((size_t)c * 256) * 8, 2048, bK);
+            bulk_g2s(Ks, Kg, K_BYTES, bK);
+            mbar_expect_tx(bV, K_BYTES);
+            bulk_g2s(Vs, Vg, K_BYTES, bV);
+        }
+        __syncwarp();
+        constexpr uint32_t idescS = umma_idesc_bf16(128, 256, 0, 0);
+        constexpr uint32_t idescO = umma_idesc_bf16(128, HS, 0, 1);
+        const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks), va = smem_u32(Vs);
+#pragma unroll 1
+        for (int qt = 0; qt < 2; qt++) {
+            if (qt == 0) mbar_wait(bK, 0);
+            else {
+                mbar_wait(bE, 0);       // epilogue of tile 0 has drained O from TMEM
+                mbar_wait(bQ1, 0);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < HS / 16; ks++)
+                    umma_ss(tmem, umma_desc(qa + ks * 2 * 2048, 2048, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128), idescS,
+                            ks != 0 ? 1u : 0u);
+                umma_commit(bS);
+            }
+            __syncwarp();
+            if (qt == 0) {              // Q smem is free once S(0) has retired: fetch the second query tile
+                mbar_wait(bS, 0);
+                if (lane == 0) {
+                    mbar_expect_tx(bQ1, Q_BYTES);
+#pragma unroll
+                    for (int c = 0; c < HS / 8; c++) bulk_g2s(Qs + c * 2048, Qg + ((size_t)c * 256 + 128) * 8, 2048, bQ1);
+                }
+                __syncwarp();
+            }
+            // O = P V: A = P from TMEM (8 columns of bf16 pairs per 16 keys), B = V MN-major (16 B = 8 d of one key)
+            mbar_wait(bP, qt);
+            if (qt == 0) mbar_wait(bV, 0);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++)
+                    umma_ts(tmem + 64, tmem + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8), umma_desc(va + ks * 2 * 128, 128, 4096), idescO,
+                            ks != 0 ? 1u : 0u);
+                umma_commit(bO);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, kh = warp >> 2;
+        const int r = q * 32 + lane;  // query row within the tile
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const f32x2 sc2 = pk2(a.scale_log2e, a.scale_log2e);
+#pragma unroll 1
+        for (int qt = 0; qt < 2; qt++) {
+            mbar_wait(bS, qt);
+            tc_fence_after();
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            }
+            redm[kh * 128 + r] = mx;
+            named_bar_sync(1, 256);
+            mx = fmaxf(redm[r], redm[128 + r]);
+            const float moff = mx * a.scale_log2e;
+            const f32x2 mo2 = pk2(-moff, -moff);
+            f32x2 sum2 = pk2(0.f, 0.f);
+#pragma unroll 1
+            for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c0, v);
+                tmem_wait_ld();
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const f32x2 xs = fma2(pk2u(v[2 * j], v[2 * j + 1]), sc2, mo2);
+                    float e0, e1;
+                    if ((j & MG_ATTN_POLY_MASK) == MG_ATTN_POLY_MASK) {
+                        exp2_poly2(xs, e0, e1);
+                    } else {
+                        upk2(xs, e0, e1);
+                        e0 = ex2_approx(e0);
+                        e1 = ex2_approx(e1);
+                    }
+                    sum2 = add2(sum2, pk2(e0, e1));
+                    w[j] = pack_bf16x2(e0, e1);
+                }
+                tmem_st16(trow + kh * 128 + (c0 - kh * 128) / 2, w);   // P in place, inside this thread's own S range
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bP);
+            {
+                float s0, s1;
+                upk2(sum2, s0, s1);
+                reds[kh * 128 + r] = s0 + s1;
+            }
+            named_bar_sync(1, 256);                  // row sums exchanged; redm may be rewritten by the next tile after this point
+            const float inv = 1.0f / (reds[r] + reds[128 + r]);
+
+            mbar_wait(bO, qt);
+            tc_fence_after();
+            constexpr int DH = HS / 2;             // output columns per thread
+            uint32_t v[DH];
+            tmem_ld32(trow + 64 + kh * DH, v);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bE);                       // O is in registers: the issuer may overwrite S/O for the next tile
+            const int mt = seq * 2 + qt;
+#pragma unroll
+            for (int j = 0; j < DH / 8; j++) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+                o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+                o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+                o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+                const int col = head * HS + kh * DH + 8 * j;
+                uint4 *O = reinterpret_cast<uint4 *>(a.out) + ((size_t)mt * (a.C / 8) + col / 8) * 128 + r;
+                *O = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<256>(tmem);
+}
+template <int HS>
+constexpr int attn_ts_smem_bytes() { return 128 * HS * 2 + 2 * 256 * HS * 2 + 4 * 128 * 4 + 7 * 8 + 16; }
+
+// ---------------------------------------------------------------------------------------------
 // attn_persistent_kernel (head size 32): persistent CTAs (2 per SM) looping over (sequence, head) items with
 // double-buffered Q/K/V in smem -- the loads of the NEXT item are in flight during the softmax of the current one -- and
 // the probabilities kept in TENSOR MEMORY: each thread converts its row of S in place to bf16 pairs (tcgen05.st) and the
