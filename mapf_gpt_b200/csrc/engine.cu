@@ -168,7 +168,7 @@ static int upload_f32(const float *src, size_t n, float **out)
     return MG_OK;
 }
 
-// the same for gemm_pair_kernel: [N/BN][2 halves][K/8][BN/2][8], CTA r of a pair streams rows [r * BN/2, (r+1) * BN/2) of the tile
+// the same for gemm_pair_persistent_kernel: [N/BN][2 halves][K/8][BN/2][8], CTA r of a pair streams rows [r * BN/2, (r+1) * BN/2) of the tile
 static int upload_packed_pair(const float *W, int N, int K, int BN, __nv_bfloat16 **out)
 {
     std::vector<uint16_t> h((size_t)N * K);
@@ -311,42 +311,6 @@ static int launch_gemm_cfg(mg_engine *e, const GemmArgs &a, int kc)
     CU(cudaGetLastError());
     return MG_OK;
 }
-template <int EPI, int BN>
-static int launch_gemm_pair(mg_engine *e, const GemmArgs &a, int kc)
-{
-    constexpr int BK = 64, STAGES = BN == 256 ? 3 : 4;
-    // MAPF_GPT_B200_GEMM_PAIR_1CTA=1 (hang hunt): pad the dynamic shared memory so that only ONE CTA fits per SM
-    static const bool one_cta = getenv("MAPF_GPT_B200_GEMM_PAIR_1CTA") != nullptr;
-    const int smem = one_cta ? 120 * 1024 : gemm_pair_smem_bytes<BN, BK, STAGES>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(gemm_pair_kernel<BN, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((a.M / 128) * (a.N / BN));
-    cfg.blockDim = dim3(320);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = e->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    static const bool dbg = getenv("MAPF_GPT_B200_DEBUG_SYNC") != nullptr;   // hang hunt: name every launch, wait for it
-    if (dbg) fprintf(stderr, "gemm_pair EPI %d M %d N %d K %d ...", EPI, a.M, a.N, a.K);
-    prof_begin(e, kc);
-    CU(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN, BK, STAGES, EPI>, a));
-    prof_end(e);
-    if (dbg) {
-        CU(cudaStreamSynchronize(e->stream));
-        fprintf(stderr, " done\n");
-    }
-    CU(cudaGetLastError());
-    return MG_OK;
-}
 // persistent CTA-pair GEMM (gemm_pair_persistent_kernel): one pair per SM pair, two TMEM accumulators
 template <int EPI>
 static int launch_gemm_pair_persistent(mg_engine *e, const GemmArgs &a, int kc)
@@ -386,17 +350,11 @@ template <int EPI>
 static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 {
     if (a.M % 128) return fail(MG_ERR_ARG, "gemm: M=%d not a multiple of 128", a.M);
-    // MAPF_GPT_B200_GEMM_PAIR: 2 (default) = persistent CTA pairs, one pair per SM pair, two TMEM accumulators (+18 % on the 85M step);
-    // 0 = the single-CTA kernel; 1 = the non-persistent pair kernel, an experiment kept for the record: with two pairs co-resident per
-    // SM pair its first c_fc launch of a process hung intermittently on a warmed-up GPU.
-    const char *pair_env = getenv("MAPF_GPT_B200_GEMM_PAIR");
-    static const int pair_mode = pair_env ? atoi(pair_env) : 2;
-    static const bool pair_on = pair_mode == 1;
-    static const bool pair_persistent = pair_mode == 2;
-    if (e && a.Wp && pair_persistent && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
+    // CTA pairs (gemm_pair_persistent_kernel) whenever the pair packing exists: 256-wide tiles, an even number of 128-row tiles.
+    // MAPF_GPT_B200_GEMM_PAIR=0 selects the single-CTA kernel (A/B).
+    static const bool pair_off = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0';
+    if (e && a.Wp && !pair_off && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
         return launch_gemm_pair_persistent<EPI>(e, a, kc);
-    if (e && a.Wp && pair_on && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI, 256>(e, a, kc);
-    if (e && a.Wp && pair_on && BN == 128 && a.N % 128 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0) return launch_gemm_pair<EPI, 128>(e, a, kc);
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
     if (BN == 256 && a.N % 256 == 0 && a.K % 64 == 0) return launch_gemm_cfg<256, 64, 2, EPI>(e, a, kc);
@@ -409,7 +367,6 @@ static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
 }
 static int pick_bn(int C)
 {
-    if (C % 128 == 0 && getenv("MAPF_GPT_B200_BN128") != nullptr) return 128;   // hang hunt / A-B of the generic GEMM tile width
     if (C % 256 == 0) return 256;
     if (C % 160 == 0) return 160;
     if (C % 128 == 0) return 128;
@@ -1027,8 +984,7 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         const char *np = getenv("MAPF_GPT_B200_NO_PRUNE");
         e->prune_last = !(np && np[0] == '1');
     }
-    const char *pair_env = getenv("MAPF_GPT_B200_GEMM_PAIR");
-    const bool pair_gemm = !m.fused && (BN == 256 || BN == 128) && (pair_env ? atoi(pair_env) : 2) != 0;
+    const bool pair_gemm = !m.fused && BN == 256 && !(getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0');
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;

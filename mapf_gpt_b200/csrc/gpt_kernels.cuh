@@ -19,7 +19,7 @@ enum { EPI_STORE_F32 = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_GELU = 3 };
 struct GemmArgs {
     const __nv_bfloat16 *A;  // A_ti
     const __nv_bfloat16 *W;  // W_ti packed for this BN
-    const __nv_bfloat16 *Wp; // the same weights packed for CTA pairs (gemm_pair_kernel), or nullptr
+    const __nv_bfloat16 *Wp; // the same weights packed for CTA pairs (gemm_pair_persistent_kernel), or nullptr
     void *out;               // see epilogues
     int M, N, K;             // M % 128 == 0, N % BN == 0, K % BK == 0
     int C, n_head, hs;       // EPI_QKV only
@@ -304,121 +304,18 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same GEMM on CTA PAIRS (cta_group::2): C[256 x BN] per pair = two adjacent 128-row tiles, ONE M = 256 UMMA per k-step
-// issued by the leader; A = each CTA's own rows, B = BN/2 weight rows from each CTA's ring.  Per CTA and k-block the ring
-// takes 128 x BK of A + BN/2 x BK of W instead of 128 x BK + BN x BK: at BN = 256 the L2 -> SM traffic per FLOP drops by a
-// third and a third stage fits (ncu, C = 768: the single-CTA kernel pulls 87-116 GB per launch through L2 -> SM and stalls
-// there).  Eight epilogue warps (two per TMEM lane quadrant, half of the columns each); the residual epilogue fetches x
-// one 32-column chunk ahead of the accumulator it is added to.  Protocol as post_attn_kernel<.., CL = 2>: the peer's UMMA
-// warp relays "my stage landed" to the leader, the leader's commits are multicast to both CTAs.
+// The generic path's GEMM on CTA PAIRS (cta_group::2), persistent: ONE CTA pair per SM pair (cluster of 2, 1 CTA per SM, the
+// whole shared memory as a STAGES-deep ring) looping over 256 x BN output tiles (n-tiles of the same 256 rows first, so that
+// concurrently running pairs share A in L2).  Per k-block the leader issues M = 256 UMMAs: A = each CTA's own 128 rows, B =
+// BN/2 weight rows from each CTA's ring, so a CTA streams 128 x BK of A + BN/2 x BK of W instead of 128 x BK + BN x BK (the
+// single-CTA kernel pulls 87-116 GB per launch through L2 -> SM at C = 768 and stalls there).  TWO accumulator buffers in
+// TMEM (2 x BN columns): the 8 epilogue warps of both CTAs drain buffer b while the leader's UMMAs fill buffer b ^ 1.
+// Protocol as post_attn_kernel<.., CL = 2>: the peer's UMMA warp relays "my stage landed" to the leader, the leader's commits
+// are multicast to both CTAs; on top of the ring acc_full[2] (multicast commit) and, on the leader, acc_empty[2] (one elected
+// arrive per epilogue warp of both CTAs = 16).  W is packed [N/BN][2 halves][K/8][BN/2][8] (upload_packed_pair).
+// (A non-persistent version with two pairs co-resident per SM pair hung intermittently in its first c_fc launch of a process
+// -- M = 256, N = 256 UMMAs from two pairs on one SM pair -- and was removed; DESIGN.md has the record, commit 55da32f the code.)
 // warps 0-7: epilogue, warp 8: bulk-copy producer, warp 9: UMMA issuer (leader) / relay (peer).
-// W is packed [N/BN][2 halves][K/8][BN/2][8] (upload_packed_pair).
-// ---------------------------------------------------------------------------------------------
-template <int BN, int BK, int STAGES, int EPI>
-__global__ void __launch_bounds__(320, 2) gemm_pair_kernel(const GemmArgs a)
-{
-    constexpr int A_BYTES = BK * 256;            // [BK/8][128][16 B]
-    constexpr int B_BYTES = BK * (BN / 2) * 2;   // [BK/8][BN/2][16 B]: this CTA's half of the weight rows
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    constexpr int HALF = BN / 2;                 // accumulator columns per epilogue warp
-    static_assert(BN % 64 == 0 && BN <= 256, "gemm_pair_kernel: BN in {64, 128, 192, 256}");
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
-    uint64_t *empty = full + STAGES;
-    uint64_t *pfull = empty + STAGES;            // leader only: the peer's stage landed (relayed)
-    uint64_t *acc_bar = pfull + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
-    uint32_t *qkv_off = tmem_slot + 2;           // EPI_QKV: uint4 offset of each 8-column group inside a sequence's q/k/v block
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();
-    const bool leader = crank == 0;
-    const int NT = a.N / BN;
-    const int pair = blockIdx.x >> 1;
-    const int nt = pair % NT, mt = (pair / NT) * 2 + (int)crank;
-    const int KB = a.K / BK;
-    if constexpr (EPI == EPI_QKV) {
-        if (threadIdx.x < BN / 8) {
-            const int n = nt * BN + 8 * threadIdx.x;
-            const int which = n / a.C, rem = n - which * a.C;
-            const int head = rem / a.hs, d0 = rem - head * a.hs;
-            qkv_off[threadIdx.x] = (uint32_t)(((which * a.n_head + head) * (a.hs / 8) + d0 / 8) * 256);
-        }
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-            mbar_init(&pfull[s], 1);
-        }
-        mbar_init(acc_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 9) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 8) {
-        if (lane == 0) {
-            const __nv_bfloat16 *srcA = a.A + (size_t)mt * (a.K / 8) * 1024;
-            const __nv_bfloat16 *srcB = a.Wp + ((size_t)nt * 2 + crank) * (a.K / 8) * (HALF * 8);
-            for (int kb = 0; kb < KB; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                uint8_t *st = smem + s * STAGE_BYTES;
-                bulk_g2s(st, srcA + (size_t)kb * (BK / 8) * 1024, A_BYTES, &full[s]);
-                bulk_g2s(st + A_BYTES, srcB + (size_t)kb * (BK / 8) * (HALF * 8), B_BYTES, &full[s]);
-            }
-        }
-    } else if (warp == 9 && !leader) {
-        for (int kb = 0; kb < KB; kb++) {   // relay: my half of stage kb has landed
-            const int s = kb % STAGES;
-            mbar_wait(&full[s], (kb / STAGES) & 1);
-            if (lane == 0) mbar_arrive_cluster(&pfull[s], 0);
-            __syncwarp();
-        }
-    } else if (warp == 9) {
-        constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
-        for (int kb = 0; kb < KB; kb++) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            mbar_wait(&pfull[s], ph);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-            const uint32_t sb = sa + A_BYTES;
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < BK / 16; ks++)
-                    umma_ss_pair(tmem, umma_desc(sa + ks * 2 * 2048, 2048, 128), umma_desc(sb + ks * 2 * (HALF * 16), HALF * 16, 128),
-                                 idesc, (kb | ks) != 0 ? 1u : 0u);
-                umma_commit_pair(&empty[s], (uint16_t)3);   // frees the stage in both CTAs when these UMMAs retire
-                if (kb == KB - 1) umma_commit_pair(acc_bar, (uint16_t)3);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ---- epilogue: TMEM lane quadrant = warp & 3, column half = warp >> 2
-        pair_epilogue<BN, EPI>(a, mt, nt, tmem, warp, lane, qkv_off, [&]() { mbar_wait(acc_bar, 0); tc_fence_after(); }, []() {});
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();           // neither CTA leaves (or frees TMEM) while the pair's UMMAs / commits may still target it
-    if (warp == 9) tmem_dealloc_pair<TMEM_COLS>(tmem);
-}
-// ---------------------------------------------------------------------------------------------
-// Persistent form: ONE CTA pair per SM pair (1 CTA per SM, the whole shared memory as a STAGES-deep ring), looping over
-// 256 x BN output tiles (n-tiles of the same 256 rows first, so concurrently running pairs share A in L2), TWO accumulator
-// buffers in TMEM (2 x BN columns): the 8 epilogue warps of both CTAs drain buffer b while the leader's UMMAs fill buffer b ^ 1.
-// No two pairs ever share an SM pair (the non-persistent kernel above hung intermittently with two co-resident pairs issuing
-// M = 256, N = 256 UMMAs).  Barriers on top of the ring: acc_full[2] (multicast commit) and, on the leader,
-// acc_empty[2] (one elected arrive per epilogue warp of both CTAs = 16).
 // ---------------------------------------------------------------------------------------------
 template <int BN, int BK, int STAGES, int EPI>
 __global__ void __launch_bounds__(320, 1) gemm_pair_persistent_kernel(const GemmArgs a)
@@ -547,8 +444,6 @@ __global__ void __launch_bounds__(320, 1) gemm_pair_persistent_kernel(const Gemm
 template <int BN, int BK, int STAGES>
 constexpr int gemm_pair_persistent_smem_bytes(int N) { return STAGES * (BK * 256 + BK * (BN / 2) * 2) + (3 * STAGES + 4) * 8 + 16 + (N / 8) * 4; }
 
-template <int BN, int BK, int STAGES>
-constexpr int gemm_pair_smem_bytes() { return STAGES * (BK * 256 + BK * (BN / 2) * 2) + (3 * STAGES + 1) * 8 + 16 + (BN / 8) * 4; }
 
 template <int BN, int BK, int STAGES>
 constexpr int gemm_smem_bytes() { return STAGES * (BK * 256 + BK * BN * 2) + (2 * STAGES + 1) * 8 + 16 + (BN / 8) * 4; }
