@@ -352,7 +352,7 @@ static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
     if (a.M % 128) return fail(MG_ERR_ARG, "gemm: M=%d not a multiple of 128", a.M);
     // CTA pairs (gemm_pair_persistent_kernel) whenever the pair packing exists: 256-wide tiles, an even number of 128-row tiles.
     // MAPF_GPT_B200_GEMM_PAIR=0 selects the single-CTA kernel (A/B).
-    static const bool pair_off = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0';
+    const bool pair_off = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0';   // per launch: tests flip it
     if (e && a.Wp && !pair_off && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
         return launch_gemm_pair_persistent<EPI>(e, a, kc);
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
@@ -424,7 +424,7 @@ static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cu
 }
 static int launch_attn(mg_engine *e, const AttnArgs &a, int hs, int n_seq, cudaStream_t st)
 {
-    static const bool classic = getenv("MAPF_GPT_B200_ATTN_CLASSIC") != nullptr;
+    const bool classic = getenv("MAPF_GPT_B200_ATTN_CLASSIC") != nullptr;   // read per launch: tests flip it between engines
     if (hs == 32 && !classic) return launch_attn_persistent(e, a, n_seq, st);
     if (hs == 32) return launch_attn_hs<32>(e, a, n_seq, st);
     if (hs == 64 && !classic) {   // probabilities in TMEM, two CTAs per SM (attn_ts_kernel)

@@ -238,6 +238,31 @@ def test_block0_lookup_table_is_bit_identical_to_the_computed_block0(dev, name, 
     assert np.array_equal(outs[0], outs[1])
 
 
+def test_generic_path_kernel_variants_agree(dev, monkeypatch):
+    """C = 768 (85M shape, 2 layers to keep it short): persistent CTA-pair GEMMs + TMEM-resident probabilities (defaults) against the
+    single-CTA GEMM and the smem-P attention kernel.  Same bf16 operands and fp32 accumulation order per output element; the
+    attention variants differ in where the row sum is taken (fp32 threads vs bf16 tensor core), hence a tolerance, not equality."""
+    from mapf_gpt_b200 import engine as E, weights as W
+    cfg = W.GPTConfig(block_size=256, vocab_size=67, n_layer=2, n_head=12, n_embd=768, dropout=0.0, bias=False)
+    sd = W.scale_weights(W.perturb_layernorm(W.random_init(cfg)), 3.0)
+    toks = np.random.default_rng(9).integers(0, 67, (66, 256)).astype(np.int8)
+    outs = {}
+    for name, env in (("default", {}), ("single_cta_gemm", {"MAPF_GPT_B200_GEMM_PAIR": "0"}), ("smem_p_attention", {"MAPF_GPT_B200_ATTN_CLASSIC": "1"})):
+        for k in ("MAPF_GPT_B200_GEMM_PAIR", "MAPF_GPT_B200_ATTN_CLASSIC"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = E.RolloutEngine(1, 1, 11, 11)
+        eng.load_model(sd, cfg)
+        outs[name] = eng.forward_tokens(toks)
+        eng.close()
+    assert np.abs(outs["default"] - outs["single_cta_gemm"]).max() < 1e-3
+    assert np.abs(outs["default"] - outs["smem_p_attention"]).max() < 2e-2
+    from oracle import gpt_oracle as G
+    ref = G.forward_logits(sd, cfg.n_layer, cfg.n_head, torch.from_numpy(toks.astype(np.int64)))[:, :5].numpy()
+    assert np.abs(outs["default"] - ref).max() < LOGIT_TOL
+
+
 # ------------------------------------------------------------------------------------------------ large maps (SURVEY 8f.1)
 def _big_grid(seed=0, h=150, w=170, p=0.18):
     from mapf_gpt_b200 import maps
