@@ -40,9 +40,11 @@ extern "C" {
 #define MG_ERR_CUDA (-2)    /* CUDA runtime error or no device                      */
 #define MG_ERR_STATE (-3)   /* call order (e.g. act before reset / load_model)      */
 #define MG_ERR_VOCAB (-4)   /* a value left the token vocabulary (int_vocab.at throws, cpp:357-361) */
+#define MG_ERR_NUMERIC (-5) /* a logit is not finite (torch.multinomial raises on inf/nan probabilities, model.py:257) */
 
 #define MG_CONTEXT 256      /* tokens per observation (cpp:386-387, inference.py:22) */
 #define MG_VOCAB 67         /* App. A of SURVEY.md                                   */
+#define MG_METRIC_COLS 10   /* doubles per slot written by mg_engine_get_metrics     */
 
 /* InputParameters, observation_generator.h:22-40 (field order of the pybind ctor) */
 typedef struct mg_params {
@@ -99,6 +101,9 @@ size_t mg_model_num_floats(const mg_model_config *cfg);
 int mg_engine_reset(mg_engine *e, int first_env, int n_envs, int n_agents,
                     const uint8_t *obstacles, const int32_t *pos_xy, const int32_t *goal_xy);
 int mg_engine_num_envs(const mg_engine *e);   /* highest reset slot + 1 */
+/* MAPFGPTInference.reset_states (inference.py:174-177) forgets every env slot but keeps the model: drops all slots (num_envs
+ * becomes 0) while the loaded weights, the workspace and the per-map precompute tables of large maps stay on the device. */
+int mg_engine_clear(mg_engine *e);
 
 /* ---- the four verbs of the reference generator, batched over all reset slots -------- */
 /* update_agents (cpp:432-485).  Any pointer may be NULL = "keep what the device holds"
@@ -149,8 +154,9 @@ int mg_engine_get_cost2go(mg_engine *e, int env, int agent, uint16_t *out_hw);  
 /* Cost2GoPartial (observation_generator.h:67-82): window bounds {left,right,top,bottom} (inclusive) and the rows x cols
  * field of one agent; returns rows*cols (negative on error).  Works for every grid size. */
 int mg_engine_get_partial(mg_engine *e, int env, int agent, int32_t *bounds4, uint16_t *out, int cap);
-/* per-slot episode metrics, doubles [num_envs][8]:
- * 0 ep_length, 1 CSR, 2 ISR, 3 SoC, 4 makespan, 5 agents on goal now, 6 agent-steps executed, 7 n_agents */
+/* per-slot episode metrics, doubles [num_envs][MG_METRIC_COLS]:
+ * 0 ep_length, 1 CSR, 2 ISR, 3 SoC, 4 makespan, 5 agents on goal now, 6 agent-steps executed, 7 n_agents,
+ * 8 avg_agents_density (pogema AgentsDensityWrapper, experiment_setup/create_env.py:36-40), 9 observations averaged in 8 */
 int mg_engine_get_metrics(mg_engine *e, double *out);
 int mg_engine_synchronize(mg_engine *e);
 /* CUDA-event time of the last mg_engine_rollout / mg_engine_act call in ms, and per-phase
@@ -178,6 +184,14 @@ int mg_test_gemm(int device, const void *A_bf16, const void *B_bf16, float *C, i
  * attention kernel.  q,k,v,out: bf16 [n_seq][n_head][256][hs] row-major device pointers. */
 int mg_test_attention(int device, const void *q, const void *k, const void *v, void *out,
                       int n_seq, int n_head, int hs);
+/* the same with the kernel variant chosen explicitly: 0 = max-subtracting softmax, 1 = max-free softmax on pre-scaled q (the
+ * engine's default; the hook multiplies q by log2(e)/sqrt(hs) first, as the engine folds that factor into Wq), 2 = the
+ * classic one-CTA-per-item kernel */
+int mg_test_attention_ex(int device, const void *q, const void *k, const void *v, void *out,
+                         int n_seq, int n_head, int hs, int variant);
+/* precision mode of engines created afterwards by this process: 0 = bf16 tensor-core path (default), 1 = fp32 CUDA-core
+ * verification path (also selected by MAPF_GPT_B200_PRECISION=fp32); returns the previous value */
+int mg_set_precision(int mode);
 
 /* UMMA-rate microbenchmark: average ms per launch of the production GEMM kernel (tile width BN) on dummy operands */
 int mg_test_gemm_time(int device, int M, int N, int K, int BN, int iters, float *ms);

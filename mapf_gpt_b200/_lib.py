@@ -14,7 +14,8 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("MAPF_GPT_B200_LIB_PATH") or _HERE / "libmapf_gpt_b200.so")
 _lib = None
 
-MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_STATE, MG_ERR_VOCAB = 0, -1, -2, -3, -4
+MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_STATE, MG_ERR_VOCAB, MG_ERR_NUMERIC = 0, -1, -2, -3, -4, -5
+MG_METRIC_COLS = 10
 
 
 class MgParams(C.Structure):  # mg_params == InputParameters (observation_generator.h:22-40)
@@ -52,6 +53,7 @@ _SIGS = {
     "mg_model_num_floats": (C.c_size_t, [C.POINTER(MgModelConfig)]),
     "mg_engine_reset": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_engine_num_envs": (C.c_int, [C.c_void_p]),
+    "mg_engine_clear": (C.c_int, [C.c_void_p]),
     "mg_engine_update_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_engine_generate_observations": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mg_engine_act": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -83,6 +85,8 @@ _SIGS = {
     "mg_test_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mg_test_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mg_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mg_test_attention_ex": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mg_set_precision": (C.c_int, [C.c_int]),
 }
 
 EXPORTED = sorted(_SIGS)

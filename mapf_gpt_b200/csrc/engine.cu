@@ -16,6 +16,7 @@
 #include "env_kernels.cuh"
 #include "gpt_kernels.cuh"
 #include "fused_kernels.cuh"
+#include "precise_kernels.cuh"
 
 using namespace mg;
 
@@ -38,6 +39,23 @@ static int fail(int code, const char *fmt, ...)
             return fail(MG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+
+// cudaFuncSetAttribute / occupancy results are PER DEVICE: a process may drive several GPUs (MAPFGPTInference on cuda:0 and
+// cuda:1), so "done once" flags are kept per device index.  The attribute is set BEFORE the flag, so a racing thread at worst
+// sets it twice.
+#include <atomic>
+static const int MG_MAX_DEVICES = 64;
+struct PerDevice {
+    std::atomic<int> v[MG_MAX_DEVICES];
+    PerDevice() { for (auto &x : v) x.store(0); }
+};
+static int cur_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= MG_MAX_DEVICES) ? 0 : d;
+}
+
 // ------------------------------------------------------------------------------------------- model
 enum KernelClass { KC_BFS = 0, KC_OBSERVE, KC_EMBED, KC_LN, KC_QKV, KC_ATTN, KC_PROJ, KC_FC, KC_PROJ2, KC_HEAD, KC_STEP, KC_POST, KC_ATTN_LAST, KC_POST_LAST, KC_COUNT };
 
@@ -54,6 +72,7 @@ struct Model {
     int BN = 0, BK = 0, hs = 0;
     bool fused = false;   // C in {160, 256}: post_attn_kernel replaces proj / ln_2 / fc / proj2 / next ln_1
     bool fuse_qkv = false;  // ... and the next block's c_attn
+    float q_fold = 1.f;     // log2(e) / sqrt(hs), multiplied into the q rows of every c_attn weight at load time
     float *wte = nullptr, *wpe = nullptr, *lnf = nullptr;
     float *wpe_ti = nullptr;   // wpe re-tiled [2][C/4][128][4] for embed_ln_kernel
     uint4 *tab0 = nullptr;     // block 0 as a lookup: [67 tokens][256 positions][C/4 + 3C/8] 16-byte groups (x, then q|k|v)
@@ -102,6 +121,14 @@ struct mg_engine {
     bool use_tma = false;
     int n_sms = 148;
     long long kc_n[KC_COUNT] = {0};
+    std::vector<int32_t> h_nag;        // host mirror of s.nag (range checks of host-supplied positions / goals)
+    // attention softmax: the max-free kernels (scores pre-scaled into the log2 domain by the folded Wq) run until a step
+    // produces a non-finite logit; that step is redone with the max-subtracting kernels, which then stay on
+    bool safe_softmax = false;
+    int precise = 0;                   // MAPF_GPT_B200_PRECISION=fp32: fp32 CUDA-core verification forward (precise_kernels.cuh)
+    float *pw = nullptr;               // precise path: the raw fp32 checkpoint buffer on the device
+    float *p_ws = nullptr;             // precise path: workspace
+    size_t p_ws_floats = 0;
 };
 
 static void prof_begin(mg_engine *e, int kc)
@@ -189,8 +216,9 @@ static int upload_packed_pair(const float *W, int N, int K, int BN, __nv_bfloat1
 // CTA r of a pair copies one contiguous half-stage holding rows [r * rows/2, (r+1) * rows/2) of every unit.
 // LayerNorm gains are folded into the weights that consume the normalised activations (the kernel then writes plain
 // (x - mean) * rstd): ln_2's gain g2[k] scales column k of Wfc, the next block's ln_1 gain gn[k] scales column k of Wqkv_next.
+// qscale: the attention scale folded into the q rows (rows < C) of the next block's c_attn (Model::q_fold).
 static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, const float *Wqkv_next,
-                                   const float *g2, const float *gn, int C, int split, __nv_bfloat16 **out)
+                                   const float *g2, const float *gn, int C, int split, float qscale, __nv_bfloat16 **out)
 {
     const int HC = C / 2, NCH = 8, NPROJ = C / 16, NFC = C / 32, NP2 = HC / 16;
     const int U = C == 160 ? 5 : 4;              // units per stage (PostAttnCfg::U)
@@ -232,7 +260,8 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
             for (int kb = 0; kb < NFC; kb++, st++)
                 for (int n = 0; n < HC; n++)
                     for (int k = 0; k < 32; k++)
-                        put_kn(st * stage_elems, k / 8, HC, n, k % 8, Wqkv_next[(size_t)(hh * HC + n) * C + kb * 32 + k] * gn[kb * 32 + k]);
+                        put_kn(st * stage_elems, k / 8, HC, n, k % 8,
+                               Wqkv_next[(size_t)(hh * HC + n) * C + kb * 32 + k] * gn[kb * 32 + k] * (hh * HC + n < C ? qscale : 1.f));
     CU(dalloc(out, total));
     CU(cudaMemcpy(*out, h.data(), total * 2, cudaMemcpyHostToDevice));
     return MG_OK;
@@ -245,10 +274,10 @@ template <int C, int NT, int UU = 0, int CL = 1>
 static int launch_post_attn_c(mg_engine *e, PostAttnArgs a, int MT, int kc)
 {
     using K = PostAttnCfg<C, NT, UU, CL>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (const int d = cur_device(); !attr_set.v[d].load()) {
         CU(cudaFuncSetAttribute(post_attn_kernel<C, NT, UU, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
-        attr_set = true;
+        attr_set.v[d].store(1);
     }
     prof_begin(e, kc);
     if (CL == 1) {
@@ -299,10 +328,10 @@ template <int BN, int BK, int STAGES, int EPI>
 static int launch_gemm_cfg(mg_engine *e, const GemmArgs &a, int kc)
 {
     constexpr int smem = gemm_smem_bytes<BN, BK, STAGES>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (const int d = cur_device(); !attr_set.v[d].load()) {
         CU(cudaFuncSetAttribute(gemm_kernel<BN, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.v[d].store(1);
     }
     const int tiles = (a.M / 128) * (a.N / BN);
     if (e) prof_begin(e, kc);
@@ -319,11 +348,13 @@ static int launch_gemm_pair_persistent(mg_engine *e, const GemmArgs &a, int kc)
     const int smem = gemm_pair_persistent_smem_bytes<BN, BK, STAGES>(a.N);
     constexpr int SMEM_MAX = 224 * 1024;
     if (smem > SMEM_MAX) return fail(MG_ERR_ARG, "gemm: N=%d too wide for the persistent pair kernel", a.N);
-    static int max_clusters = 0;
+    static PerDevice max_clusters_dev;
+    const int dev = cur_device();
+    int max_clusters = max_clusters_dev.v[dev].load();
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(320);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = e->stream;
+    cfg.stream = e ? e->stream : 0;   // e == nullptr: test hook (mg_test_gemm)
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
@@ -337,12 +368,13 @@ static int launch_gemm_pair_persistent(mg_engine *e, const GemmArgs &a, int kc)
         int n = 0;
         CU(cudaOccupancyMaxActiveClusters(&n, gemm_pair_persistent_kernel<BN, BK, STAGES, EPI>, &cfg));
         max_clusters = n > 0 ? n : 1;
+        max_clusters_dev.v[dev].store(max_clusters);
     }
     const int n_tiles = (a.M / 256) * (a.N / BN);
     cfg.gridDim = dim3(2 * std::min(max_clusters, n_tiles));
-    prof_begin(e, kc);
+    if (e) prof_begin(e, kc);
     CU(cudaLaunchKernelEx(&cfg, gemm_pair_persistent_kernel<BN, BK, STAGES, EPI>, a));
-    prof_end(e);
+    if (e) prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
 }
@@ -353,7 +385,7 @@ static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
     // CTA pairs (gemm_pair_persistent_kernel) whenever the pair packing exists: 256-wide tiles, an even number of 128-row tiles.
     // MAPF_GPT_B200_GEMM_PAIR=0 selects the single-CTA kernel (A/B).
     const bool pair_off = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0';   // per launch: tests flip it
-    if (e && a.Wp && !pair_off && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
+    if (a.Wp && !pair_off && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
         return launch_gemm_pair_persistent<EPI>(e, a, kc);
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
@@ -377,10 +409,10 @@ template <int HS>
 static int launch_attn_hs(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream_t st)
 {
     constexpr int smem = attn_smem_bytes<HS>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (const int d = cur_device(); !attr_set.v[d].load()) {
         CU(cudaFuncSetAttribute(attn_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.v[d].store(1);
     }
     if (e) prof_begin(e, KC_ATTN);
     attn_kernel<HS><<<n_seq * a.n_head, 288, smem, st>>>(a);
@@ -388,58 +420,67 @@ static int launch_attn_hs(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream
     CU(cudaGetLastError());
     return MG_OK;
 }
+template <bool FAST>
 static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream_t st)
 {
     constexpr int smem = attn_persistent_smem_bytes();
-    static bool attr_set = false;
-    static int n_sms = 148;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(attn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
+    static PerDevice attr_set, n_sms_dev;
+    const int dev = cur_device();
+    if (!attr_set.v[dev].load()) {
+        CU(cudaFuncSetAttribute(attn_persistent_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        n_sms_dev.v[dev].store(n);
+        attr_set.v[dev].store(1);
     }
+    const int n_sms = n_sms_dev.v[dev].load();
     const int n_items = n_seq * a.n_head;
     AttnArgs aa = a;
+    int *tmp_ctr = nullptr;
     if (e) {
         if (!e->d_attn_ctr) {
             CU(dalloc(&e->d_attn_ctr, 2));
             CU(cudaMemsetAsync(e->d_attn_ctr, 0, 8, st));
         }
         aa.work_counter = e->d_attn_ctr;
-    } else {   // test hook without an engine: one synchronous caller at a time
-        static int *ctr = nullptr;
-        if (!ctr) {
-            CU(dalloc(&ctr, 2));
-            CU(cudaMemset(ctr, 0, 8));
-        }
-        aa.work_counter = ctr;
+    } else {   // test hook without an engine: a counter of its own, freed after the (synchronous) call
+        CU(dalloc(&tmp_ctr, 2));
+        CU(cudaMemsetAsync(tmp_ctr, 0, 8, st));
+        aa.work_counter = tmp_ctr;
     }
     if (e) prof_begin(e, KC_ATTN);
-    attn_persistent_kernel<<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(aa, n_items);
+    attn_persistent_kernel<FAST><<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(aa, n_items);
+    if (e) prof_end(e);
+    CU(cudaGetLastError());
+    if (tmp_ctr) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(tmp_ctr);
+    }
+    return MG_OK;
+}
+template <bool FAST>
+static int launch_attn_ts64(mg_engine *e, const AttnArgs &a, int n_seq, cudaStream_t st)
+{   // head size 64: probabilities in TMEM, two CTAs per SM (attn_ts_kernel)
+    constexpr int smem = attn_ts_smem_bytes<64>();
+    static PerDevice attr_set;
+    if (const int d = cur_device(); !attr_set.v[d].load()) {
+        CU(cudaFuncSetAttribute(attn_ts_kernel<64, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set.v[d].store(1);
+    }
+    if (e) prof_begin(e, KC_ATTN);
+    attn_ts_kernel<64, FAST><<<n_seq * a.n_head, 288, smem, st>>>(a);
     if (e) prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
 }
-static int launch_attn(mg_engine *e, const AttnArgs &a, int hs, int n_seq, cudaStream_t st)
+// `fast`: the scores arrive in the log2 domain (scale folded into Wq) and the max-free kernels may be used; otherwise the
+// max-subtracting kernels run with a.scale_log2e (1.0 when the scale is folded).
+static int launch_attn(mg_engine *e, const AttnArgs &a, int hs, int n_seq, cudaStream_t st, bool fast)
 {
     const bool classic = getenv("MAPF_GPT_B200_ATTN_CLASSIC") != nullptr;   // read per launch: tests flip it between engines
-    if (hs == 32 && !classic) return launch_attn_persistent(e, a, n_seq, st);
+    if (hs == 32 && !classic) return fast ? launch_attn_persistent<true>(e, a, n_seq, st) : launch_attn_persistent<false>(e, a, n_seq, st);
     if (hs == 32) return launch_attn_hs<32>(e, a, n_seq, st);
-    if (hs == 64 && !classic) {   // probabilities in TMEM, two CTAs per SM (attn_ts_kernel)
-        constexpr int smem = attn_ts_smem_bytes<64>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU(cudaFuncSetAttribute(attn_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
-        if (e) prof_begin(e, KC_ATTN);
-        attn_ts_kernel<64><<<n_seq * a.n_head, 288, smem, st>>>(a);
-        if (e) prof_end(e);
-        CU(cudaGetLastError());
-        return MG_OK;
-    }
+    if (hs == 64 && !classic) return fast ? launch_attn_ts64<true>(e, a, n_seq, st) : launch_attn_ts64<false>(e, a, n_seq, st);
     if (hs == 64) return launch_attn_hs<64>(e, a, n_seq, st);
     return fail(MG_ERR_ARG, "attention: head size %d unsupported (32 or 64)", hs);
 }
@@ -477,11 +518,62 @@ static void launch_ln(mg_engine *e, const float *X, const float *gain, __nv_bflo
     else ln_kernel<<<MT, 128, 0, e->stream>>>(X, gain, out, C);
 }
 
+// ------------------------------------------------------------------------------------------- fp32 verification forward
+static int g_precision = 0;   // mg_set_precision
+// tokens (device, uint8 [n_seq][256]) -> logits (device, fp32 [n_seq][8]) on the CUDA cores in fp32 (precise_kernels.cuh)
+static int forward_precise(mg_engine *e, const uint8_t *tokens, int n_seq, float *logits)
+{
+    const Model &m = e->model;
+    const int C = m.cfg.n_embd, H = m.cfg.n_head, hs = m.hs, L = m.cfg.n_layer;
+    const size_t CC = (size_t)C * C;
+    const int chunk = std::min(n_seq, 32);
+    const size_t Mc = (size_t)chunk * 256, need = Mc * C * 10;
+    if (need > e->p_ws_floats) {
+        cudaFree(e->p_ws);
+        e->p_ws = nullptr; e->p_ws_floats = 0;
+        CU(dalloc(&e->p_ws, need));
+        e->p_ws_floats = need;
+    }
+    float *X = e->p_ws, *XN = X + Mc * C, *QKV = XN + Mc * C, *ATT = QKV + Mc * 3 * C, *HID = ATT + Mc * C;
+    const float *wte = e->pw, *wpe = wte + (size_t)MG_VOCAB * C, *lw = wpe + (size_t)256 * C;
+    const float *lnf = lw + (size_t)L * (2 * C + 12 * CC);
+    if (hs == 32) CU(cudaFuncSetAttribute(p_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, p_attn_smem_bytes<32>()));
+    else CU(cudaFuncSetAttribute(p_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, p_attn_smem_bytes<64>()));
+    auto gemm = [&](int epi, const float *A, const float *W, float *Cm, int M, int N, int K) {
+        const dim3 grid((N + 63) / 64, M / 64);
+        e->launches++;
+        if (epi == P_EPI_STORE) p_gemm_kernel<P_EPI_STORE><<<grid, 256, 0, e->stream>>>(A, W, Cm, M, N, K);
+        else if (epi == P_EPI_RESID) p_gemm_kernel<P_EPI_RESID><<<grid, 256, 0, e->stream>>>(A, W, Cm, M, N, K);
+        else p_gemm_kernel<P_EPI_GELU><<<grid, 256, 0, e->stream>>>(A, W, Cm, M, N, K);
+    };
+    for (int s0 = 0; s0 < n_seq; s0 += chunk) {
+        const int ns = std::min(chunk, n_seq - s0), M = ns * 256;
+        e->launches += 2 + 3 * L;
+        p_embed_kernel<<<(M + 7) / 8, 256, 0, e->stream>>>(tokens + (size_t)s0 * 256, wte, wpe, X, C, M);
+        for (int l = 0; l < L; l++) {
+            const float *ln1 = lw + (size_t)l * (2 * C + 12 * CC), *wqkv = ln1 + C, *wproj = wqkv + 3 * CC, *ln2 = wproj + CC,
+                        *wfc = ln2 + C, *wproj2 = wfc + 4 * CC;
+            p_ln_kernel<<<(M + 7) / 8, 256, 0, e->stream>>>(X, ln1, XN, C, M);
+            gemm(P_EPI_STORE, XN, wqkv, QKV, M, 3 * C, C);
+            if (hs == 32) p_attn_kernel<32><<<ns * H, 256, p_attn_smem_bytes<32>(), e->stream>>>(QKV, ATT, H, C);
+            else p_attn_kernel<64><<<ns * H, 256, p_attn_smem_bytes<64>(), e->stream>>>(QKV, ATT, H, C);
+            gemm(P_EPI_RESID, ATT, wproj, X, M, C, C);
+            p_ln_kernel<<<(M + 7) / 8, 256, 0, e->stream>>>(X, ln2, XN, C, M);
+            gemm(P_EPI_GELU, XN, wfc, HID, M, 4 * C, C);
+            gemm(P_EPI_RESID, HID, wproj2, X, M, C, 4 * C);
+        }
+        p_head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(X, lnf, wte, logits + (size_t)s0 * 8, C, ns);
+    }
+    CU(cudaGetLastError());
+    return MG_OK;
+}
+
 // tokens (device, uint8 [n_seq][256]) -> logits (device, fp32 [n_seq][8])
 static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float *logits)
 {
     Model &m = e->model;
     if (!m.loaded) return fail(MG_ERR_STATE, "forward: no model loaded (mg_engine_load_model)");
+    if (e->precise) return forward_precise(e, tokens, n_seq, logits);
     int rc = ensure_workspace(e, n_seq);
     if (rc) return rc;
     Workspace &w = e->ws;
@@ -513,10 +605,11 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 if (last && e->prune_last) {
                     // last block: Q / attention / c_proj / MLP only for token 255 of each sequence (App. D.2)
                     prof_begin(e, KC_ATTN_LAST);
+                    // q carries log2(e) / sqrt(hs) (Model::q_fold): ln(2) brings q k^T back to natural-log units
                     if (hs == 32)
-                        last_attn_kernel<32><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 1.0f / std::sqrt((float)hs));
+                        last_attn_kernel<32><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 0.6931471805599453f);
                     else
-                        last_attn_kernel<64><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 1.0f / std::sqrt((float)hs));
+                        last_attn_kernel<64><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 0.6931471805599453f);
                     prof_end(e);
                     PostAttnArgs pa{};
                     pa.att = w.ATTc; pa.x = w.Xc; pa.wstream = L.wstream; pa.wstream_pair = L.wstream_pair; pa.ln2_gain = L.ln2;
@@ -528,11 +621,11 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 }
                 AttnArgs at{};
                 at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
-                at.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
+                at.scale_log2e = 1.0f;   // folded into Wq (Model::q_fold)
                 at.timeline = e->d_timeline;
                 static const int stamp_item = getenv("MAPF_GPT_B200_STAMP_ITEM") ? atoi(getenv("MAPF_GPT_B200_STAMP_ITEM")) : 40;
                 at.dbg_variant = stamp_item;   // which item of a persistent attention CTA tools/timeline.py stamps
-                if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
+                if ((rc = launch_attn(e, at, hs, ns, e->stream, !e->safe_softmax))) return rc;
                 PostAttnArgs pa{};
                 pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.wstream_pair = L.wstream_pair; pa.ln2_gain = L.ln2;
                 pa.next_gain = last ? nullptr : m.layers[l + 1].ln1;
@@ -562,8 +655,8 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
             AttnArgs at{};
             at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
-            at.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
-            if ((rc = launch_attn(e, at, hs, ns, e->stream))) return rc;
+            at.scale_log2e = 1.0f;   // folded into Wq (Model::q_fold)
+            if ((rc = launch_attn(e, at, hs, ns, e->stream, !e->safe_softmax))) return rc;
             g = GemmArgs{};
             g.A = w.ATT; g.W = L.wproj; g.Wp = L.wproj_p; g.out = w.X; g.M = M; g.N = C; g.K = C;
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ))) return rc;
@@ -751,6 +844,28 @@ static int check_vocab(mg_engine *e)
     }
     return MG_OK;
 }
+// Reads and clears both device flags after the stream has drained.  *numeric = 1 when sample_step_kernel saw a non-finite logit.
+static int read_flags(mg_engine *e, int *vocab, int *numeric)
+{
+    int32_t v[2] = {0, 0};
+    CU(cudaMemcpyAsync(v, e->s.vocab_err, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (v[0] || v[1]) CU(cudaMemsetAsync(e->s.vocab_err, 0, 8, e->stream));
+    *vocab = v[0]; *numeric = v[1];
+    return MG_OK;
+}
+// A non-finite logit after a device-resident rollout cannot be redone (the envs have moved on): the engine switches to the
+// max-subtracting softmax kernels for every later call and reports the rollout as failed.
+static int numeric_failure(mg_engine *e)
+{
+    if (!e->safe_softmax && !e->precise) {
+        e->safe_softmax = true;
+        return fail(MG_ERR_NUMERIC, "a logit was not finite: an attention score left the range of the max-free softmax "
+                                    "(|s| < ~69 nats); the engine now uses the max-subtracting kernels -- reset and rerun "
+                                    "(MAPF_GPT_B200_SAFE_SOFTMAX=1 selects them from the start)");
+    }
+    return fail(MG_ERR_NUMERIC, "a logit was not finite (inf/nan weights?): torch.multinomial would raise here (model.py:257)");
+}
 
 // Pure UMMA issue/execute rate: operands stay in smem (zero-filled), one thread issues `iters` x 4 UMMAs (M128 x N x K16,
 // SS operands, no-swizzle K-major), then commits; out[0] = clock64 cycles from first issue to completion.
@@ -800,6 +915,29 @@ static int run_umma_rate(int iters, int ctas, long long *d_out, long long *h_out
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h_out, d_out, 16, cudaMemcpyDeviceToHost));
     return MG_OK;
+}
+
+// host-supplied positions / goals of every reset slot, padded [n_envs][N][2]: the same rule as mg_engine_reset (the kernels
+// index the grid and seed the BFS with them unchecked)
+static int check_xy(const mg_engine *e, const int32_t *pos_xy, const int32_t *goal_xy)
+{
+    const EnvState &s = e->s;
+    for (int k = 0; k < e->n_envs; k++)
+        for (int a = 0; a < e->h_nag[k]; a++) {
+            const size_t i = ((size_t)k * s.N + a) * 2;
+            if (pos_xy && (pos_xy[i] < 5 || pos_xy[i + 1] < 5 || pos_xy[i] >= s.H - 5 || pos_xy[i + 1] >= s.W - 5))
+                return fail(MG_ERR_ARG, "env %d agent %d: position (%d,%d) outside the padded grid %dx%d", k, a, pos_xy[i],
+                            pos_xy[i + 1], s.H, s.W);
+            if (goal_xy && (goal_xy[i] < 0 || goal_xy[i + 1] < 0 || goal_xy[i] >= s.H || goal_xy[i + 1] >= s.W))
+                return fail(MG_ERR_ARG, "env %d agent %d: goal (%d,%d) outside the grid %dx%d", k, a, goal_xy[i], goal_xy[i + 1],
+                            s.H, s.W);
+        }
+    return MG_OK;
+}
+__global__ void scale_bf16_kernel(__nv_bfloat16 *x, size_t n, float f)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = __float2bfloat16(__bfloat162float(x[i]) * f);
 }
 
 // =========================================================================================== C ABI
@@ -871,15 +1009,19 @@ mg_engine *mg_engine_create(int device, int max_envs, int max_agents, int H, int
     ok = ok && dalloc(&s.logits, EN * 8) == cudaSuccess;
     ok = ok && dalloc(&s.steps, (size_t)s.E) == cudaSuccess && dalloc(&s.done, (size_t)s.E) == cudaSuccess;
     ok = ok && dalloc(&s.arrive, EN) == cudaSuccess && dalloc(&s.agent_steps, (size_t)s.E) == cudaSuccess;
-    ok = ok && dalloc(&s.vocab_err, 1) == cudaSuccess;
+    ok = ok && dalloc(&s.vocab_err, 2) == cudaSuccess;
+    ok = ok && dalloc(&s.density_sum, (size_t)s.E) == cudaSuccess && dalloc(&s.density_n, (size_t)s.E) == cudaSuccess;
     ok = ok && dalloc(&e->d_pos_in, EN * 2) == cudaSuccess && dalloc(&e->d_goal_in, EN * 2) == cudaSuccess;
     ok = ok && dalloc(&e->d_act_in, EN) == cudaSuccess && dalloc(&e->d_step_act, EN) == cudaSuccess;
-    ok = ok && dalloc(&e->d_q, EN * 5) == cudaSuccess && dalloc(&e->d_metrics, (size_t)s.E * 8) == cudaSuccess;
+    ok = ok && dalloc(&e->d_q, EN * 5) == cudaSuccess && dalloc(&e->d_metrics, (size_t)s.E * MG_METRIC_COLS) == cudaSuccess;
     if (ok) {
         cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
         cudaMemset(s.nag, 0, s.E * 4);
         cudaMemset(s.active, 1, s.E);
-        cudaMemset(s.vocab_err, 0, 4);
+        cudaMemset(s.vocab_err, 0, 8);
+        cudaMemset(s.density_sum, 0, s.E * 4);
+        cudaMemset(s.density_n, 0, s.E * 4);
+        e->h_nag.assign((size_t)s.E, 0);
         cudaMemset(s.tokens, 66, EN * 256);
         cudaMemset(s.logits, 0, EN * 8 * 4);
         cudaMemset(s.dirty, 0, EN);
@@ -924,6 +1066,7 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(s.obst); cudaFree(s.loc); cudaFree(s.c2g); cudaFree(s.pos); cudaFree(s.goal); cudaFree(s.hist);
     cudaFree(s.nextb); cudaFree(s.act); cudaFree(s.nag); cudaFree(s.dirty); cudaFree(s.tokens); cudaFree(s.logits);
     cudaFree(s.active); cudaFree(s.steps); cudaFree(s.done); cudaFree(s.arrive); cudaFree(s.agent_steps); cudaFree(s.vocab_err);
+    cudaFree(s.density_sum); cudaFree(s.density_n); cudaFree(e->pw); cudaFree(e->p_ws);
     cudaFree(e->d_pos_in); cudaFree(e->d_goal_in); cudaFree(e->d_act_in); cudaFree(e->d_step_act); cudaFree(e->d_q);
     cudaFree(e->d_metrics);
     Model &m = e->model;
@@ -963,6 +1106,17 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
     Model &m = e->model;
     if (m.loaded) return fail(MG_ERR_STATE, "a model is already loaded in this engine");
     m.cfg = *cfg; m.BN = BN; m.hs = hs;
+    {
+        const char *ss = getenv("MAPF_GPT_B200_SAFE_SOFTMAX"), *pr = getenv("MAPF_GPT_B200_PRECISION");
+        e->safe_softmax = ss && ss[0] == '1';
+        e->precise = (g_precision == 1 || (pr && strcmp(pr, "fp32") == 0)) ? 1 : 0;
+        if (pr && strcmp(pr, "fp32") != 0 && strcmp(pr, "bf16") != 0)
+            return fail(MG_ERR_ARG, "MAPF_GPT_B200_PRECISION=%s: expected bf16 (default) or fp32", pr);
+        if (e->precise) {   // the verification forward reads the checkpoint as it is
+            CU(dalloc(&e->pw, n_floats));
+            CU(cudaMemcpy(e->pw, w, n_floats * 4, cudaMemcpyHostToDevice));
+        }
+    }
     const size_t CC = (size_t)C * C;
     int rc;
     if ((rc = upload_f32(w, (size_t)MG_VOCAB * C, &m.wte))) return rc;
@@ -985,11 +1139,16 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         e->prune_last = !(np && np[0] == '1');
     }
     const bool pair_gemm = !m.fused && BN == 256 && !(getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0');
+    // attention scale folded into Wq: q' = (log2(e) / sqrt(hs)) q, so S = Q' K^T is already the exponent of 2 (gpt_kernels.cuh,
+    // "max-free softmax"); the fold happens in fp32, before the one bf16 rounding of the weight
+    m.q_fold = (float)(1.4426950408889634 / std::sqrt((double)hs));
+    std::vector<float> wq_s(3 * CC);
     for (auto &L : m.layers) {
         if ((rc = upload_f32(w, C, &L.ln1))) return rc;
         w += C;
-        if ((rc = upload_packed(w, 3 * C, C, BN, &L.wqkv))) return rc;
-        if (pair_gemm && (rc = upload_packed_pair(w, 3 * C, C, BN, &L.wqkv_p))) return rc;
+        for (size_t i = 0; i < 3 * CC; i++) wq_s[i] = i < CC ? w[i] * m.q_fold : w[i];
+        if ((rc = upload_packed(wq_s.data(), 3 * C, C, BN, &L.wqkv))) return rc;
+        if (pair_gemm && (rc = upload_packed_pair(wq_s.data(), 3 * C, C, BN, &L.wqkv_p))) return rc;
         w += 3 * CC;
         const float *wproj = w;
         if ((rc = upload_packed(w, C, C, BN, &L.wproj))) return rc;
@@ -1012,8 +1171,8 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
             const float *wqkv_next = has_next ? w + C : nullptr;     // skip ln_1[C] of the next block
             m.fuse_qkv = getenv("MAPF_GPT_B200_NO_QKV_FUSION") == nullptr;
             const float *gn = has_next ? w : nullptr;                 // ln_1 gain of the next block
-            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, g2, gn, C, 1, &L.wstream))) return rc;
-            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, g2, gn, C, 2, &L.wstream_pair))) return rc;
+            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, g2, gn, C, 1, m.q_fold, &L.wstream))) return rc;
+            if ((rc = upload_post_attn_stream(wproj, wfc, wproj2, m.fuse_qkv ? wqkv_next : nullptr, g2, gn, C, 2, m.q_fold, &L.wstream_pair))) return rc;
         }
     }
     if ((rc = upload_f32(w, C, &m.lnf))) return rc;
@@ -1045,6 +1204,21 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
 }
 
 int mg_engine_num_envs(const mg_engine *e) { return e ? e->n_envs : 0; }
+
+int mg_engine_clear(mg_engine *e)
+{
+    if (!e) return fail(MG_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    EnvState &s = e->s;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemsetAsync(s.nag, 0, (size_t)s.E * 4, e->stream));
+    CU(cudaMemsetAsync(s.active, 1, (size_t)s.E, e->stream));
+    CU(cudaMemsetAsync(s.vocab_err, 0, 8, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    std::fill(e->h_nag.begin(), e->h_nag.end(), 0);
+    e->n_envs = 0;
+    return MG_OK;
+}
 
 int mg_engine_reset(mg_engine *e, int first_env, int n_envs, int n_agents, const uint8_t *obstacles,
                     const int32_t *pos_xy, const int32_t *goal_xy)
@@ -1097,6 +1271,9 @@ int mg_engine_reset(mg_engine *e, int first_env, int n_envs, int n_agents, const
     CU(cudaMemsetAsync(s.steps + eo, 0, n_envs * 4, e->stream));
     CU(cudaMemsetAsync(s.done + eo, 0, n_envs, e->stream));
     CU(cudaMemsetAsync(s.agent_steps + eo, 0, n_envs * 8, e->stream));
+    CU(cudaMemsetAsync(s.density_sum + eo, 0, n_envs * 4, e->stream));
+    CU(cudaMemsetAsync(s.density_n + eo, 0, n_envs * 4, e->stream));
+    for (int k = 0; k < n_envs; k++) e->h_nag[first_env + k] = n_agents;
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
     e->n_envs = std::max(e->n_envs, first_env + n_envs);
     return launch_fields(e, first_env, n_envs, 0);
@@ -1109,6 +1286,7 @@ int mg_engine_update_agents(mg_engine *e, const int32_t *pos_xy, const int32_t *
     CU(cudaSetDevice(e->device));
     EnvState &s = e->s;
     const size_t EN = (size_t)e->n_envs * s.N;
+    if (int rc = check_xy(e, pos_xy, goal_xy)) return rc;
     if (pos_xy) CU(cudaMemcpyAsync(e->d_pos_in, pos_xy, EN * 8, cudaMemcpyHostToDevice, e->stream));
     if (goal_xy) CU(cudaMemcpyAsync(e->d_goal_in, goal_xy, EN * 8, cudaMemcpyHostToDevice, e->stream));
     if (actions) CU(cudaMemcpyAsync(e->d_act_in, actions, EN * 4, cudaMemcpyHostToDevice, e->stream));
@@ -1166,9 +1344,16 @@ int mg_engine_act(mg_engine *e, int mode, const float *q_exp, int32_t *actions_o
     EnvState &s = e->s;
     const size_t EN = (size_t)e->n_envs * s.N;
     if (mode == 2) CU(cudaMemcpyAsync(e->d_q, q_exp, EN * 5 * 4, cudaMemcpyHostToDevice, e->stream));
-    int rc = forward_device(e, s.tokens, (int)EN, s.logits);
-    if (rc) return rc;
-    if ((rc = launch_step(e, mode, 0, e->d_q, nullptr))) return rc;
+    int rc;
+    for (int attempt = 0;; attempt++) {
+        if ((rc = forward_device(e, s.tokens, (int)EN, s.logits))) return rc;
+        if ((rc = launch_step(e, mode, 0, e->d_q, nullptr))) return rc;
+        int vocab = 0, numeric = 0;
+        if ((rc = read_flags(e, &vocab, &numeric))) return rc;
+        if (!numeric) break;
+        if (attempt == 0 && !e->safe_softmax && !e->precise) { e->safe_softmax = true; continue; }   // redo with the max-subtracting kernels
+        return numeric_failure(e);
+    }
     if (actions_out) CU(cudaMemcpyAsync(actions_out, s.act, EN * 4, cudaMemcpyDeviceToHost, e->stream));
     if (logits_out) {
         std::vector<float> tmp(EN * 8);
@@ -1184,6 +1369,9 @@ int mg_engine_act(mg_engine *e, int mode, const float *q_exp, int32_t *actions_o
 int mg_engine_forward_tokens(mg_engine *e, const int8_t *tokens, int n_rows, float *logits_out)
 {
     if (!e || !tokens || !logits_out || n_rows < 1) return fail(MG_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < (size_t)n_rows * 256; i++)   // nn.Embedding raises IndexError on ids outside the table (model.py:174)
+        if (tokens[i] < 0 || tokens[i] >= MG_VOCAB)
+            return fail(MG_ERR_VOCAB, "row %zu token %zu: id %d outside the vocabulary [0, %d)", i / 256, i % 256, (int)tokens[i], MG_VOCAB);
     CU(cudaSetDevice(e->device));
     Workspace &w = e->ws;
     cudaFree(w.tok); cudaFree(w.logits);
@@ -1250,6 +1438,7 @@ int mg_engine_act_host(mg_engine *e, const int32_t *pos_xy, const int32_t *goal_
     CU(cudaSetDevice(e->device));
     EnvState &s = e->s;
     const size_t EN = (size_t)e->n_envs * s.N;
+    if (int rc0 = check_xy(e, pos_xy, goal_xy)) return rc0;
     CU(cudaEventRecord(e->ev_t0, e->stream));
     if (pos_xy) CU(cudaMemcpyAsync(e->d_pos_in, pos_xy, EN * 8, cudaMemcpyHostToDevice, e->stream));
     if (goal_xy) CU(cudaMemcpyAsync(e->d_goal_in, goal_xy, EN * 8, cudaMemcpyHostToDevice, e->stream));
@@ -1260,20 +1449,22 @@ int mg_engine_act_host(mg_engine *e, const int32_t *pos_xy, const int32_t *goal_
                                                            goal_xy ? e->d_goal_in : nullptr, nullptr);
     }
     int rc;
-    if ((goal_xy || (pos_xy && s.large)) && (rc = launch_fields(e, 0, e->n_envs, 1))) return rc;
+    // large maps: agents moved on the device (mg_engine_env_step) may have left their windows even when no host array is given
+    if ((goal_xy || s.large) && (rc = launch_fields(e, 0, e->n_envs, 1))) return rc;
     if ((rc = launch_observe(e, true, true))) return rc;
-    if ((rc = forward_device(e, s.tokens, (int)EN, s.logits))) return rc;
-    if ((rc = launch_step(e, mode, 0, e->d_q, nullptr))) return rc;
-    CU(cudaMemcpyAsync(actions_out, s.act, EN * 4, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaEventRecord(e->ev_t1, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    if (e->profiling) prof_collect(e);
-    int32_t v = 0;
-    CU(cudaMemcpy(&v, s.vocab_err, 4, cudaMemcpyDeviceToHost));
-    if (v) {
-        cudaMemset(s.vocab_err, 0, 4);
-        return fail(MG_ERR_VOCAB, "a relative position left the token vocabulary");
+    int vocab = 0, numeric = 0;
+    for (int attempt = 0;; attempt++) {
+        if ((rc = forward_device(e, s.tokens, (int)EN, s.logits))) return rc;
+        if ((rc = launch_step(e, mode, 0, e->d_q, nullptr))) return rc;
+        CU(cudaMemcpyAsync(actions_out, s.act, EN * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(e->ev_t1, e->stream));
+        if ((rc = read_flags(e, &vocab, &numeric))) return rc;
+        if (!numeric) break;
+        if (attempt == 0 && !e->safe_softmax && !e->precise) { e->safe_softmax = true; continue; }   // redo with the max-subtracting kernels
+        return numeric_failure(e);
     }
+    if (e->profiling) prof_collect(e);
+    if (vocab) return fail(MG_ERR_VOCAB, "a relative position left the token vocabulary");
     return MG_OK;
 }
 
@@ -1340,7 +1531,7 @@ int mg_engine_get_metrics(mg_engine *e, double *out)
     CU(cudaSetDevice(e->device));
     e->launches++;
     metrics_kernel<<<(e->s.E + 127) / 128, 128, 0, e->stream>>>(e->s, e->d_metrics);
-    CU(cudaMemcpyAsync(out, e->d_metrics, (size_t)e->n_envs * 8 * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(out, e->d_metrics, (size_t)e->n_envs * MG_METRIC_COLS * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return MG_OK;
 }
@@ -1349,8 +1540,11 @@ int mg_engine_synchronize(mg_engine *e)
 {
     if (!e) return fail(MG_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
-    CU(cudaStreamSynchronize(e->stream));
+    int vocab = 0, numeric = 0, rc;
+    if ((rc = read_flags(e, &vocab, &numeric))) return rc;
     if (e->profiling) prof_collect(e);
+    if (numeric) return numeric_failure(e);
+    if (vocab) return fail(MG_ERR_VOCAB, "a relative position left the token vocabulary");
     return MG_OK;
 }
 
@@ -1476,9 +1670,19 @@ int mg_test_gemm(int device, const void *A, const void *B, float *C, int M, int 
     pack_rows_kernel<<<(unsigned)(((size_t)N * K + th - 1) / th), th>>>((const __nv_bfloat16 *)B, Bt, N, K, BN);
     GemmArgs g{};
     g.A = At; g.W = Bt; g.out = C; g.M = M; g.N = N; g.K = K; g.dbg_swap_lbo_sbo = (variant >> 8) & 1;
+    __nv_bfloat16 *Bp = nullptr;
+    if (variant & 0x10) {   // the persistent CTA-pair kernel (the 85M path's GEMM): B in the pair packing
+        if (cfg != 1 || (M / 128) % 2) { cudaFree(At); cudaFree(Bt); return fail(MG_ERR_ARG, "test gemm: the pair kernel needs cfg 1 and M % 256 == 0"); }
+        std::vector<uint16_t> hb((size_t)N * K);
+        CU(cudaMemcpy(hb.data(), B, hb.size() * 2, cudaMemcpyDeviceToHost));
+        std::vector<float> hf(hb.size());
+        for (size_t i = 0; i < hb.size(); i++) { const uint32_t u = (uint32_t)hb[i] << 16; memcpy(&hf[i], &u, 4); }
+        if (int rc = upload_packed_pair(hf.data(), N, K, BN, &Bp)) { cudaFree(At); cudaFree(Bt); return rc; }
+        g.Wp = Bp;
+    }
     int rc = launch_gemm<EPI_STORE_F32>(nullptr, BN, g, 0);
     cudaError_t err = cudaDeviceSynchronize();
-    cudaFree(At); cudaFree(Bt);
+    cudaFree(At); cudaFree(Bt); cudaFree(Bp);
     if (rc) return rc;
     if (err != cudaSuccess) return fail(MG_ERR_CUDA, "test gemm: %s", cudaGetErrorString(err));
     return MG_OK;
@@ -1532,8 +1736,19 @@ int mg_test_gemm_time(int device, int M, int N, int K, int BN, int iters, float 
 }
 
 // q,k,v,out: bf16 [n_seq][n_head][256][hs] row-major
+int mg_set_precision(int mode)
+{
+    const int prev = g_precision;
+    if (mode == 0 || mode == 1) g_precision = mode;
+    return prev;
+}
 int mg_test_attention(int device, const void *q, const void *k, const void *v, void *out, int n_seq, int n_head, int hs)
 {
+    return mg_test_attention_ex(device, q, k, v, out, n_seq, n_head, hs, 0);
+}
+int mg_test_attention_ex(int device, const void *q, const void *k, const void *v, void *out, int n_seq, int n_head, int hs, int variant)
+{
+    if (variant < 0 || variant > 2) return fail(MG_ERR_ARG, "test attention: variant must be 0, 1 or 2");
     CU(cudaSetDevice(device));
     const int C = n_head * hs;
     const size_t per = (size_t)n_seq * n_head * 256 * hs;
@@ -1551,7 +1766,16 @@ int mg_test_attention(int device, const void *q, const void *k, const void *v, v
     AttnArgs a{};
     a.qkv = qkv; a.out = att; a.n_head = n_head; a.C = C;
     a.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hs));
-    int rc = launch_attn(nullptr, a, hs, n_seq, 0);
+    if (variant == 1) {   // the engine folds the scale into Wq; here q itself is scaled (one extra bf16 rounding of q)
+        for (int s = 0; s < n_seq; s++) {
+            const size_t nq = (size_t)n_head * 256 * hs;
+            scale_bf16_kernel<<<(unsigned)((nq + th - 1) / th), th>>>(qkv + (size_t)s * 3 * nq, nq, a.scale_log2e);
+        }
+        a.scale_log2e = 1.0f;
+    }
+    if (variant == 2) setenv("MAPF_GPT_B200_ATTN_CLASSIC", "1", 1);
+    int rc = launch_attn(nullptr, a, hs, n_seq, 0, variant == 1);
+    if (variant == 2) unsetenv("MAPF_GPT_B200_ATTN_CLASSIC");
     // att is A_ti [M/128][C/8][128][8] with column = head*hs + d -> out [seq][head][256][hs]
     __nv_bfloat16 *rm = nullptr;
     CU(dalloc(&rm, per));

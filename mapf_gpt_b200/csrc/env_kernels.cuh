@@ -45,7 +45,9 @@ struct EnvState {
     uint8_t *done;       // [E]
     int32_t *arrive;     // [E][N] step at which the agent last arrived on its goal, -1 = not on goal
     unsigned long long *agent_steps;  // [E]
-    int32_t *vocab_err;  // [1]
+    float *density_sum;  // [E] sum over observations of the mean agents-per-traversable-FOV-cell (avg_agents_density)
+    int32_t *density_n;  // [E] observations summed (reset observation + one per executed step)
+    int32_t *vocab_err;  // [2]: [0] a relative position left the vocabulary, [1] a logit was not finite
 };
 
 __constant__ int c_moves[5][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
@@ -680,6 +682,43 @@ __device__ __forceinline__ float exp1_from_bits(uint32_t b)
 //   (3) episode counters (App. C.4-C.5).
 // mode: 0 greedy, 1 philox, 2 supplied q, 3 = actions already in s.act (host supplied).
 // ------------------------------------------------------------------------------------------------
+// avg_agents_density (pogema's AgentsDensityWrapper; experiment_setup/create_env.py:36-40 wraps every eval env with it;
+// SURVEY App. C.5 -- recollection of an un-vendored dependency, parity unpinned): for one observation, the mean over agents of
+//   (agents inside the agent's 11x11 FOV, itself included) / (traversable cells of that FOV).
+// One warp per agent, a lane per 4 window cells.  Called by all threads of the block; returns the env's mean in thread 0.
+__device__ __forceinline__ float fov_density(const EnvState &s, int e, int n, float *scratch /* [8] shared */)
+{
+    const int cells = s.H * s.P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int16_t *loc = s.loc + (size_t)e * cells;
+    const uint8_t *ob = s.obst + (size_t)e * cells;
+    float acc = 0.f;
+    for (int i = warp; i < n; i += nw) {
+        const short2 p = s.pos[e * s.N + i];
+        int ag = 0, fr = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int w = lane + 32 * t;
+            if (w < 121) {
+                const int wi = w / 11, wj = w - wi * 11;
+                const int c = (p.x - 5 + wi) * s.P + (p.y - 5 + wj);
+                ag += loc[c] >= 0 ? 1 : 0;
+                fr += ob[c] == 0 ? 1 : 0;
+            }
+        }
+        ag = __reduce_add_sync(0xffffffffu, ag);
+        fr = __reduce_add_sync(0xffffffffu, fr);
+        acc += (float)ag / (float)max(fr, 1);
+    }
+    __syncthreads();
+    if (lane == 0) scratch[warp] = acc;
+    __syncthreads();
+    float tot = 0.f;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < nw; w++) tot += scratch[w];
+    return tot / (float)n;
+}
+
 struct StepArgs {
     int mode;
     int do_step;
@@ -709,6 +748,9 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
             const int idx = e * s.N + i;
             const float *l = s.logits + (size_t)idx * 8;
             const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3], l4 = l[4];
+            // torch.multinomial raises on inf / nan probabilities (model.py:257); here the flag also tells the engine that
+            // the max-free attention softmax left its range (engine.cu: safe_softmax)
+            if (!(isfinite(l0) && isfinite(l1) && isfinite(l2) && isfinite(l3) && isfinite(l4))) atomicExch(s.vocab_err + 1, 1);
             const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
             float p[5] = {expf(l0 - mx), expf(l1 - mx), expf(l2 - mx), expf(l3 - mx), expf(l4 - mx)};
             const float sum = (((p[0] + p[1]) + p[2]) + p[3]) + p[4];
@@ -736,6 +778,11 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
     }
     if (!a.do_step || frozen) return;
     __syncthreads();
+    __shared__ float dens_scratch[8];
+    if (t_now == 0) {   // the observation env.reset() returned
+        const float d0 = fov_density(s, e, n, dens_scratch);
+        if (threadIdx.x == 0) { s.density_sum[e] = d0; s.density_n[e] = 1; }
+    }
 
     // ---- soft collision step
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -810,6 +857,10 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
     __syncthreads();
     if (on_goal) atomicAdd(&s_on, on_goal);
     __syncthreads();
+    {   // the observation this step returns
+        const float d1 = fov_density(s, e, n, dens_scratch);
+        if (threadIdx.x == 0) { s.density_sum[e] += d1; s.density_n[e] += 1; }
+    }
     if (threadIdx.x == 0) {
         s.steps[e] = t_now + 1;
         s.agent_steps[e] += (unsigned long long)n;
@@ -817,14 +868,15 @@ __global__ void __launch_bounds__(256) sample_step_kernel(EnvState s, StepArgs a
     }
 }
 
-// per-slot metrics (App. C.5): [ep_length, CSR, ISR, SoC, makespan, on_goal_now, agent_steps, n_agents]
+// per-slot metrics (App. C.5): [ep_length, CSR, ISR, SoC, makespan, on_goal_now, agent_steps, n_agents, avg_agents_density, density samples]
+#define MG_METRIC_COLS_DEV 10
 __global__ void metrics_kernel(EnvState s, double *out)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= s.E) return;
     const int n = s.nag[e];
-    double *o = out + (size_t)e * 8;
-    if (n == 0) { for (int k = 0; k < 8; k++) o[k] = 0.0; return; }
+    double *o = out + (size_t)e * MG_METRIC_COLS_DEV;
+    if (n == 0) { for (int k = 0; k < MG_METRIC_COLS_DEV; k++) o[k] = 0.0; return; }
     const int T = s.steps[e];
     int on = 0, soc = 0, mk = 0;
     for (int i = 0; i < n; i++) {
@@ -836,6 +888,9 @@ __global__ void metrics_kernel(EnvState s, double *out)
     }
     o[0] = T; o[1] = on == n ? 1.0 : 0.0; o[2] = (double)on / n; o[3] = soc; o[4] = mk; o[5] = on;
     o[6] = (double)s.agent_steps[e]; o[7] = n;
+    const int dn = s.density_n[e];
+    o[8] = dn > 0 ? (double)s.density_sum[e] / dn : 0.0;
+    o[9] = dn;
 }
 
 }  // namespace mg

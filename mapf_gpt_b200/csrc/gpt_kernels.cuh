@@ -511,6 +511,57 @@ __device__ __forceinline__ float max3(float a, float b, float c)
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Max-free softmax (FAST attention kernels).  The engine folds (1/sqrt(hs)) * log2(e) into the q rows of every c_attn weight
+// at load time, so S = Q K^T arrives in the log2 domain and P = 2^S needs neither the row-max pass over TMEM nor the
+// per-element scale/offset FFMA2: softmax(s)_j = 2^(s_j) / sum_k 2^(s_k) for ANY common offset, and fp32 / bf16 carry the
+// same 8-bit exponent, so P and its row sum are exact to the usual rounding as long as the row's largest score stays inside
+// (-100, +127) in log2 units (+-69 nats; LayerNorm'ed inputs give |score| of a few units).  Outside that range the row
+// produces inf / NaN (overflow) or 0/0 (every key flushed to zero), which propagates to the logits, is flagged by
+// sample_step_kernel and makes the engine redo the step with the max-subtracting kernel (engine.cu: safe_softmax).
+// ---------------------------------------------------------------------------------------------
+// 2^x for a PAIR of inputs of either sign on the FMA/ALU pipes: exp2_poly2 with the argument clamped on both sides
+// (x >= 128 saturates at 2^127.99 instead of wrapping the exponent field).
+__device__ __forceinline__ void exp2_poly2_wide(uint32_t u0, uint32_t u1, float &r0, float &r1)
+{
+    const float x0 = fminf(fmaxf(__uint_as_float(u0), -125.0f), 127.99f), x1 = fminf(fmaxf(__uint_as_float(u1), -125.0f), 127.99f);
+    const f32x2 xc = pk2(x0, x1);
+    const f32x2 t = add2(xc, pk2(12582912.0f, 12582912.0f));
+    const f32x2 n = add2(t, pk2(-12582912.0f, -12582912.0f));
+    const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), xc);
+    f32x2 p = fma2(pk2(0.05508868396282196f, 0.05508868396282196f), f, pk2(0.24260404706001282f, 0.24260404706001282f));
+    p = fma2(p, f, pk2(0.6932762265205383f, 0.6932762265205383f));
+    p = fma2(p, f, pk2(0.9999289512634277f, 0.9999289512634277f));
+    uint32_t t0, t1, p0, p1;
+    upk2u(t, t0, t1);
+    upk2u(p, p0, p1);
+    r0 = __uint_as_float(p0 + (t0 << 23));
+    r1 = __uint_as_float(p1 + (t1 << 23));
+}
+// which of every 8 consecutive pairs take the polynomial instead of MUFU.EX2 in the FAST kernels (bit j & 7).  Without the
+// scale FFMA2 and the max pass a MUFU pair costs 3 issue slots and 16 XU cycles per warp, a polynomial pair ~18 issue slots:
+// the two pipes balance near 3 of 8 pairs on the polynomial.
+#ifndef MG_ATTN_POLY_BITS_FAST
+#define MG_ATTN_POLY_BITS_FAST 0xA4
+#endif
+// P = 2^S for N consecutive log2-domain scores -> N/2 packed bf16 pairs; SUM: also accumulate the fp32 row sum
+template <int N, bool SUM>
+__device__ __forceinline__ void exp2_pack_fast(const uint32_t (&v)[N], uint32_t (&w)[N / 2], f32x2 &sum2)
+{
+#pragma unroll
+    for (int j = 0; j < N / 2; j++) {
+        float e0, e1;
+        if ((MG_ATTN_POLY_BITS_FAST >> (j & 7)) & 1) {
+            exp2_poly2_wide(v[2 * j], v[2 * j + 1], e0, e1);
+        } else {
+            e0 = ex2_approx(__uint_as_float(v[2 * j]));
+            e1 = ex2_approx(__uint_as_float(v[2 * j + 1]));
+        }
+        if (SUM) sum2 = add2(sum2, pk2(e0, e1));
+        w[j] = pack_bf16x2(e0, e1);
+    }
+}
+
 // One CTA per (sequence, head): K and V are loaded once and both 128-query tiles run back to back (the second Q tile
 // is fetched while the first one is in its softmax).
 // warps 0-7: softmax (thread pair per query row: TMEM lane quadrant = warp&3, key half = warp>>2) + epilogue,
@@ -705,7 +756,7 @@ __global__ void __launch_bounds__(288, (HS <= 32 ? 2 : 1)) attn_kernel(const Att
 // tensor-pipe activity, profiles/r01e_85m_ncu.md).
 // TMEM (256 columns): S = [0,256); P (bf16x2) = [0,64) for keys 0..127 and [128,192) for keys 128..255; O = [64,64+HS).
 // ---------------------------------------------------------------------------------------------
-template <int HS>
+template <int HS, bool FAST = false>
 __global__ void __launch_bounds__(288, 2) attn_ts_kernel(const AttnArgs a)
 {
     static_assert(HS == 64, "O = [64, 64 + HS) must fit between the two P ranges");
@@ -803,6 +854,20 @@ __global__ void __launch_bounds__(288, 2) attn_ts_kernel(const AttnArgs a)
         for (int qt = 0; qt < 2; qt++) {
             mbar_wait(bS, qt);
             tc_fence_after();
+            f32x2 sum2 = pk2(0.f, 0.f);
+            if constexpr (FAST) {
+                // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S; 64 columns per TMEM round trip
+#pragma unroll 1
+                for (int cb = 0; cb < 2; cb++) {
+                    uint32_t v[64], w[32];
+                    tmem_ld32(trow + kh * 128 + cb * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                    tmem_ld32(trow + kh * 128 + cb * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                    tmem_wait_ld();
+                    exp2_pack_fast<64, true>(v, w, sum2);
+                    tmem_st16(trow + kh * 128 + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
+                    tmem_st16(trow + kh * 128 + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
+                }
+            } else {
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
@@ -817,7 +882,6 @@ __global__ void __launch_bounds__(288, 2) attn_ts_kernel(const AttnArgs a)
             mx = fmaxf(redm[r], redm[128 + r]);
             const float moff = mx * a.scale_log2e;
             const f32x2 mo2 = pk2(-moff, -moff);
-            f32x2 sum2 = pk2(0.f, 0.f);
 #pragma unroll 1
             for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
                 uint32_t v[32];
@@ -839,6 +903,7 @@ __global__ void __launch_bounds__(288, 2) attn_ts_kernel(const AttnArgs a)
                     w[j] = pack_bf16x2(e0, e1);
                 }
                 tmem_st16(trow + kh * 128 + (c0 - kh * 128) / 2, w);   // P in place, inside this thread's own S range
+            }
             }
             tmem_wait_st();
             tc_fence_before();
@@ -889,6 +954,7 @@ constexpr int attn_ts_smem_bytes() { return 128 * HS * 2 + 2 * 256 * HS * 2 + 4 
 // thread pair converts inside its own column range); [O | rowsum] = [64,112).
 // warps 0-7: softmax + epilogue, warp 8: bulk-copy producer, warp 9: UMMA issuer.
 // ---------------------------------------------------------------------------------------------
+template <bool FAST = false>
 __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs a, int n_items)
 {
     constexpr int HS = 32;
@@ -1016,6 +1082,24 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 }
                 tc_fence_after();
                 if (stamp) MG_ASTAMP(110 + 8 * qt);
+                if constexpr (FAST) {
+                    // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S; 64 columns per TMEM round trip
+                    f32x2 unused = pk2(0.f, 0.f);
+#pragma unroll 1
+                    for (int cb = 0; cb < 2; cb++) {
+                        uint32_t v[64], w[32];
+                        tmem_ld32(trow + kh * 128 + cb * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                        tmem_ld32(trow + kh * 128 + cb * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                        tmem_wait_ld();
+                        exp2_pack_fast<64, false>(v, w, unused);
+                        tmem_st16(trow + kh * 128 + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
+                        tmem_st16(trow + kh * 128 + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bP);
+                    if (stamp) MG_ASTAMP(113 + 8 * qt);
+                } else {
                 float mx = -INFINITY;
 #pragma unroll 1
                 for (int c0 = kh * 128; c0 < kh * 128 + 128; c0 += 32) {
@@ -1058,6 +1142,7 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 mbar_arrive(bP);
                 if (stamp) MG_ASTAMP(113 + 8 * qt);
                 named_bar_sync(1, 256);                  // redm may be rewritten only after everybody has read it
+                }
 
                 mbar_wait(bO, t & 1);
                 tc_fence_after();

@@ -75,6 +75,10 @@ class RolloutEngine:
     def num_envs(self) -> int:
         return self._L.mg_engine_num_envs(self._h)
 
+    def clear(self):
+        """Forget every env slot; the loaded model and the per-map tables stay on the device."""
+        _lib.check(self._L.mg_engine_clear(self._h))
+
     def reset(self, first_env: int, obstacles, pos, goal):
         """obstacles [n_envs,H,W] (or [H,W] broadcast), pos/goal [n_envs,n_agents,2]."""
         pos = np.ascontiguousarray(pos, dtype=np.int32)
@@ -189,8 +193,9 @@ class RolloutEngine:
         return (left, right, top, bottom), buf.reshape(right - left + 1, bottom - top + 1)
 
     def metrics(self) -> np.ndarray:
-        """[num_envs, 8]: ep_length, CSR, ISR, SoC, makespan, on_goal_now, agent_steps, n_agents"""
-        out = np.empty((self.num_envs, 8), dtype=np.float64)
+        """[num_envs, 10]: ep_length, CSR, ISR, SoC, makespan, on_goal_now, agent_steps, n_agents,
+        avg_agents_density, density samples"""
+        out = np.empty((self.num_envs, _lib.MG_METRIC_COLS), dtype=np.float64)
         _lib.check(self._L.mg_engine_get_metrics(self._h, _ptr(out)))
         return out
 
@@ -223,12 +228,19 @@ def test_gemm(A, B, variant: int = 0):
     return out
 
 
-def test_attention(q, k, v):
-    """torch bf16 CUDA tensors [n_seq, n_head, 256, hs] -> same shape, via the production kernel."""
+def test_attention(q, k, v, variant: int = 0):
+    """torch bf16 CUDA tensors [n_seq, n_head, 256, hs] -> same shape, via the production kernels.
+    variant 0: max-subtracting softmax, 1: max-free softmax on pre-scaled q (engine default), 2: classic kernel."""
     import torch
     n_seq, n_head, T, hs = q.shape
     assert T == 256
     out = torch.empty_like(q)
-    _lib.check(_lib.lib().mg_test_attention(q.device.index or 0, q.data_ptr(), k.data_ptr(), v.data_ptr(),
-                                            out.data_ptr(), n_seq, n_head, hs))
+    _lib.check(_lib.lib().mg_test_attention_ex(q.device.index or 0, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                               out.data_ptr(), n_seq, n_head, hs, variant))
     return out
+
+
+def set_precision(mode: str) -> str:
+    """'bf16' (tensor-core path) or 'fp32' (CUDA-core verification path) for engines created afterwards."""
+    prev = _lib.lib().mg_set_precision({"bf16": 0, "fp32": 1}[mode])
+    return "fp32" if prev == 1 else "bf16"

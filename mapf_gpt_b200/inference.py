@@ -119,9 +119,10 @@ class MAPFGPTInference:
         _lib.lib()
 
     def reset_states(self):
+        # O(1) like the reference (inference.py:174-177): the engine, its loaded model and the per-map tables stay on the
+        # device; only the env slots are forgotten.  A later episode that does not fit re-sizes the engine (_ensure_slots).
         if self._engine is not None:
-            self._engine.close()
-        self._engine = None
+            self._engine.clear()
         self._slots, self._slot_n, self._last_actions = {}, {}, {}
         self.torch_generator.manual_seed(0)
         self._step = 0
@@ -194,12 +195,16 @@ class MAPFGPTInference:
         new = [(k, o) for k, o in zip(positions, observations_list) if k not in self._slots]
         if not new:
             return
+        grids = [np.asarray(o[0]["global_obstacles"]) for o in observations_list]
+        H = max(g.shape[0] for g in grids)
+        Wd = max(g.shape[1] for g in grids)
+        N = max(len(o) for o in observations_list)
+        E = self._max_envs or len(observations_list)
+        eng = self._engine
+        if eng is not None and not self._slots and (E > eng.E or N > eng.N or H > eng.H or Wd > eng.W):
+            eng.close()                  # a fresh episode (reset_states) that outgrew the engine: size a new one
+            self._engine = None
         if self._engine is None:
-            grids = [np.asarray(o[0]["global_obstacles"]) for o in observations_list]
-            H = max(g.shape[0] for g in grids)
-            Wd = max(g.shape[1] for g in grids)
-            N = max(len(o) for o in observations_list)
-            E = self._max_envs or len(observations_list)
             params = dict(cost2go_value_limit=self.cfg.cost2go_value_limit, num_agents=self.cfg.num_agents,
                           num_previous_actions=self.cfg.num_previous_actions, context_size=self.cfg.context_size,
                           obs_radius=self.cfg.cost2go_radius, agents_radius=self.cfg.agents_radius,

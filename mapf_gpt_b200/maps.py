@@ -3,11 +3,13 @@
 The reference gets maps from eval_configs/<set>/maps.yaml through
 ToolboxRegistry.register_maps (example.py:29-32, benchmark.py:37-40) and starts/goals
 from POGEMA's own seeded sampler, which is not available offline.  This module
-holds the maps BASELINE.json names (extracted once by tools/extract_maps.py) and a
+holds every map the five eval sets name (401, extracted once by tools/extract_maps.py
+into data/maps.json.gz), accepts more through register_maps(), and has a
 deterministic sampler of our own; seeds are ours, not POGEMA's.
 """
 from __future__ import annotations
 
+import gzip
 import json
 from collections import deque
 from functools import lru_cache
@@ -16,12 +18,20 @@ from pathlib import Path
 import numpy as np
 
 OBS_RADIUS = 5  # POGEMA pads every side by obs_radius (example.py:48)
-_DATA = Path(__file__).resolve().parent / "data" / "maps.json"
+_DATA = Path(__file__).resolve().parent / "data" / "maps.json.gz"
+EVAL_CONFIGS = Path(__file__).resolve().parent / "data" / "eval_configs"   # packaged sweep descriptions (benchmark.py)
 
 
 @lru_cache(maxsize=1)
 def _maps() -> dict:
-    return json.load(open(_DATA))
+    with gzip.open(_DATA, "rt") as f:
+        return json.load(f)
+
+
+def register_maps(maps: dict, set_name: str = "user") -> None:
+    """ToolboxRegistry.register_maps (benchmark.py:37-40): {name: multi-line map string} as maps.yaml holds them."""
+    for n, txt in maps.items():
+        _maps()[n] = {"set": set_name, "rows": str(txt).split("\n")}
 
 
 def map_names() -> list[str]:

@@ -123,10 +123,15 @@ def pogema_step_soft(obstacles, positions, actions):
 
 def load_ref_module():
     """The reference's pybind module built into oracle/_ref, or None."""
+    import sys
+    for name in ("observation_generator", "mapf_gpt.observation_generator"):   # a pybind module registers its types once per
+        if name in sys.modules:                                                 # process: reuse whichever copy is loaded
+            return sys.modules[name]
     so = _HERE / "_ref" / ("observation_generator" + sysconfig.get_config_var("EXT_SUFFIX"))
     if not so.exists():
         return None
     spec = importlib.util.spec_from_file_location("observation_generator", so)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    sys.modules["observation_generator"] = mod
     return mod

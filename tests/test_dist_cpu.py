@@ -19,7 +19,9 @@ def _worker(rank, world, port, per_env, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     first, cnt = parallel.shard_range(per_env.shape[0], rank, world)
     red = parallel.reduce_metrics(parallel.local_metric_sums(per_env[first:first + cnt]))
+    table = parallel.gather_rows(per_env[first:first + cnt], per_env.shape[0], first)
     if rank == 0:
+        red["table_equal"] = bool(np.array_equal(table, per_env))
         out.put(red)
     dist.barrier()
     dist.destroy_process_group()
@@ -39,7 +41,7 @@ def test_shard_ranges_cover_exactly():
 def test_metrics_allreduce_equals_single_process_sum():
     from mapf_gpt_b200 import parallel
     rng = np.random.default_rng(0)
-    per_env = np.zeros((37, 8))
+    per_env = np.zeros((37, 10))
     per_env[:, 0] = rng.integers(10, 129, 37)
     per_env[:, 1] = rng.integers(0, 2, 37)
     per_env[:, 2] = rng.random(37)
@@ -47,6 +49,7 @@ def test_metrics_allreduce_equals_single_process_sum():
     per_env[:, 4] = rng.integers(10, 129, 37)
     per_env[:, 6] = per_env[:, 0] * 64
     per_env[:, 7] = 64
+    per_env[:, 8] = rng.random(37)
     per_env[5, 7] = 0                                    # an unused slot is ignored
     single = parallel.reduce_metrics(parallel.local_metric_sums(per_env))
     ctx = mp.get_context("spawn")
@@ -58,5 +61,6 @@ def test_metrics_allreduce_equals_single_process_sum():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert red["episodes"] == single["episodes"] == 36
+    assert red.pop("table_equal")                          # gather_rows: every rank sees every episode row
     for k in single:
         assert abs(red[k] - single[k]) < 1e-9, k

@@ -10,7 +10,7 @@ GOLD_OBS = np.load(Path(__file__).parent / "golden" / "obs_golden.npz")
 GOLD_GPT = np.load(Path(__file__).parent / "golden" / "gpt_golden.npz")
 GOLDEN = Path(__file__).parent / "golden"
 N_SCEN = len([k for k in GOLD_OBS.files if k.endswith("_tokens")])
-LOGIT_TOL = 5e-2   # bf16 operands, fp32 accumulate/residual vs the reference's fp32 (DESIGN.md "Tolerance")
+LOGIT_TOL = 2e-2   # bf16 operands, fp32 accumulate/residual vs the reference fp32; measured max 1.2e-2 (DESIGN.md "Tolerance")
 
 
 @pytest.fixture(scope="module")

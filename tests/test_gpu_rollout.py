@@ -7,7 +7,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-LOGIT_TOL = 5e-2
+LOGIT_TOL = 2e-2   # bf16 operands, fp32 accumulate/residual vs the reference fp32; measured max 1.2e-2 (DESIGN.md "Tolerance")
 
 
 def instances(name, n, envs, seed=0, first=0):
@@ -178,7 +178,7 @@ def test_dropin_adapter_matches_reference_call_pattern(built, tmp_path):
     rows = o.generate_observations().tolist()
     assert len(algo.act(rows)) == 32
     algo.reset_states()
-    assert algo._engine is None
+    assert algo._engine is not None and algo._engine.num_envs == 0   # O(1) reset: the engine and its model stay
 
 
 @pytest.mark.parametrize("name,n,envs,model", [("validation-mazes-seed-000", 64, 1024, "2M"), ("wfi_warehouse", 192, 64, "6M"),

@@ -123,3 +123,31 @@ def test_cost2go_cache_golden_is_self_consistent():
     assert g["rows"] == g["cols"] > 0
     assert g["bytes"] == 16 + 2 * g["rows"] * g["cols"]
     assert len(g["sha256"]) == 64
+
+
+def test_benchmark_yaml_axes_and_tabular_view():
+    """benchmark.py reads the sweep from eval_configs/<set>/<set>.yaml (reference benchmark.py:28-50): the packaged copies
+    expand to the reference's 3 296 episodes per model, every named map is in the store, and the tabular view averages over
+    the dropped keys."""
+    import importlib.util
+    import yaml
+    from mapf_gpt_b200 import maps
+    spec = importlib.util.spec_from_file_location("benchmark", ROOT / "benchmark.py")
+    bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bm)
+    total, names = 0, set(maps.map_names())
+    want = {"01-random": 768, "02-mazes": 768, "03-warehouse": 768, "04-movingai": 512, "05-puzzles": 480}
+    for folder in bm.FOLDERS:
+        cfg = yaml.safe_load(open(maps.EVAL_CONFIGS / folder / f"{folder}.yaml"))
+        fixed, axes, combos = bm.expand_grid_search(cfg["environment"])
+        assert len(combos) == want[folder] and "num_agents" in axes
+        assert fixed["collision_system"] == "soft" and fixed["max_episode_steps"] in (128, 256)
+        assert {({**fixed, **c})["map_name"] for c in combos} <= names
+        assert set(cfg["algorithms"]) == {"MAPF-GPT-2M", "MAPF-GPT-6M"}
+        total += len(combos)
+    assert total == 3296
+    recs = [{"algorithm": "A", "env_grid_search": {"num_agents": n, "map_name": f"m{i}"},
+             "metrics": {m: float(n + i) for m in bm.METRICS}} for n in (8, 16) for i in range(3)]
+    header, rows = bm.tabular_view(recs, {"type": "tabular", "drop_keys": ["seed", "map_name", "runtime"]}, ["num_agents", "map_name"])
+    assert header == ["algorithm", "num_agents", "CSR", "ISR", "SoC", "makespan", "ep_length", "avg_agents_density", "episodes"]
+    assert rows == [["A", 8] + [9.0] * 6 + [3], ["A", 16] + [17.0] * 6 + [3]]

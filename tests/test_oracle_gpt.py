@@ -55,3 +55,25 @@ def test_param_counts():
         cfg = W.model_config(name)
         sd = W.random_init(cfg)
         assert sum(v.numel() for k, v in sd.items() if k != "lm_head.weight") == n
+
+
+def test_oracle_rollout_equals_the_unmodified_reference_inference():
+    """oracle/cpu_rollout.py (ported forward + sampler) against the UNMODIFIED mapf_gpt/inference.py + model.py + compiled
+    generator loaded from baseline/_ref (oracle/ref_runtime.py): same obs dicts in, identical sampled actions out, step after
+    step -- pins the port of GPT.act / _forward_batch / _prepare_inputs, not only its logits."""
+    import numpy as np
+    import pytest
+    from oracle import cpu_rollout, ref_runtime
+    from mapf_gpt_b200 import maps, weights as W
+    if not ref_runtime.available():
+        pytest.skip("baseline/_ref not built (needs /root/reference once: make -C oracle baseline_ref)")
+    cfg = W.model_config("2M")
+    sd = W.scale_weights(W.perturb_layernorm(W.random_init(cfg)), 3.0)
+    m = maps.load_map("validation-random-seed-000")
+    st, gl = maps.sample_instance(m, 12, 5)
+    port = cpu_rollout.CpuRollout(m["grid"], st[None], gl[None], sd, cfg.n_layer, cfg.n_head)
+    ref = ref_runtime.ReferenceRollout(m["grid"], st[None], gl[None], sd, cfg, device="cpu", mode="act")
+    for t in range(6):
+        _, acts = port.step()
+        racts = ref.step()
+        assert (np.asarray(racts[0]) == acts[0]).all() and (ref.pos == port.pos).all(), t
