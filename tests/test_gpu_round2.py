@@ -281,14 +281,14 @@ def test_act_host_without_host_arrays_on_a_large_map(built):
     o.create_agents(st, gl)
     pos, last = st.copy(), np.full(n, -1, np.int32)
     for t in range(70):                                        # drift right: FOVs cross the 64-cell window lines
-        eng.act_host(None, None, E.MODE_GREEDY)
+        chosen = eng.act_host(None, None, E.MODE_GREEDY)
         o.update_agents(pos, gl, last)
         assert (eng.tokens()[0] == o.generate_observations()).all(), f"step {t}"
         act = np.where(rng.random(n) < 0.8, 4, rng.integers(0, 5, n)).astype(np.int32)
-        new = eng.env_step(act[None])
+        new = eng.env_step(act[None])                          # EXECUTE the drift; the history keeps the policy's own actions
         pos, _ = oracle.pogema_step_soft(grid, pos, act)
         assert (new[0] == pos).all()
-        last = act
+        last = chosen[0]
     eng.close()
 
 
