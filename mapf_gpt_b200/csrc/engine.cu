@@ -63,6 +63,7 @@ struct Layer {
     float *ln1 = nullptr, *ln2 = nullptr;
     __nv_bfloat16 *wqkv = nullptr, *wproj = nullptr, *wfc = nullptr, *wproj2 = nullptr;
     __nv_bfloat16 *wqkv_p = nullptr, *wproj_p = nullptr, *wfc_p = nullptr, *wproj2_p = nullptr;   // CTA-pair packing (generic path, BN = 256)
+    float *cs_qkv = nullptr, *cs_fc = nullptr;   // LayerNorm folded into the GEMMs: column sums of the gain-folded bf16 weights
     __nv_bfloat16 *wstream = nullptr;   // fused post-attention kernel: stage images in consumption order
     __nv_bfloat16 *wstream_pair = nullptr;   // the same stream for CTA pairs: every stage split into two N/2-row halves
 };
@@ -73,6 +74,7 @@ struct Model {
     bool fused = false;   // C in {160, 256}: post_attn_kernel replaces proj / ln_2 / fc / proj2 / next ln_1
     bool fuse_qkv = false;  // ... and the next block's c_attn
     float q_fold = 1.f;     // log2(e) / sqrt(hs), multiplied into the q rows of every c_attn weight at load time
+    bool ln_fused = false;  // generic path on CTA-pair GEMMs: ln_1 / ln_2 have no pass of their own (GemmArgs: xb_out / stats / colsum)
     float *wte = nullptr, *wpe = nullptr, *lnf = nullptr;
     float *wpe_ti = nullptr;   // wpe re-tiled [2][C/4][128][4] for embed_ln_kernel
     uint4 *tab0 = nullptr;     // block 0 as a lookup: [67 tokens][256 positions][C/4 + 3C/8] 16-byte groups (x, then q|k|v)
@@ -82,6 +84,7 @@ struct Workspace {
     int chunk_seqs = 0;
     float *X = nullptr;
     __nv_bfloat16 *XN = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr;
+    float *STATS = nullptr;           // LayerNorm folded into the GEMMs: [M/128][C/128][2][128] partial row sums / sums of squares
     float *Xc = nullptr;              // compact residual rows of token 255 (last-block pruning)
     __nv_bfloat16 *ATTc = nullptr;    // compact attention output of token 255
     uint8_t *tok = nullptr;   // staging for forward_tokens
@@ -270,34 +273,42 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
 #ifndef MG_POST_CL_DEFAULT
 #define MG_POST_CL_DEFAULT 2
 #endif
-template <int C, int NT, int UU = 0, int CL = 1>
+template <int C, int NT, int UU = 0, int CL = 1, bool PERSIST = false>
 static int launch_post_attn_c(mg_engine *e, PostAttnArgs a, int MT, int kc)
 {
     using K = PostAttnCfg<C, NT, UU, CL>;
     static PerDevice attr_set;
     if (const int d = cur_device(); !attr_set.v[d].load()) {
-        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT, UU, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        CU(cudaFuncSetAttribute(post_attn_kernel<C, NT, UU, CL, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
         attr_set.v[d].store(1);
     }
-    prof_begin(e, kc);
-    if (CL == 1) {
-        post_attn_kernel<C, NT, UU, CL><<<MT / NT, K::THREADS, K::SMEM_BYTES, e->stream>>>(a);
-    } else {
-        a.wstream = a.wstream_pair;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(MT / NT);
-        cfg.blockDim = dim3(K::THREADS);
-        cfg.dynamicSmemBytes = K::SMEM_BYTES;
-        cfg.stream = e->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, post_attn_kernel<C, NT, UU, CL>, a));
+    a.n_groups = MT / NT;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.n_groups);
+    cfg.blockDim = dim3(K::THREADS);
+    cfg.dynamicSmemBytes = K::SMEM_BYTES;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CL == 1 ? 0 : 1;
+    if (CL == 2) a.wstream = a.wstream_pair;
+    if (PERSIST) {
+        // as many CTAs (CTA pairs) as the device keeps resident, each looping over tile groups g, g + grid, ...
+        static const int grid_override = getenv("MAPF_GPT_B200_POST_GRID") ? atoi(getenv("MAPF_GPT_B200_POST_GRID")) : 0;
+        static const int stagger_override = getenv("MAPF_GPT_B200_POST_STAGGER_NS") ? atoi(getenv("MAPF_GPT_B200_POST_STAGGER_NS")) : 0;
+        int cap = grid_override > 0 ? grid_override : K::CTAS_PER_SM * e->n_sms;   // all resident CTA slots (a late CTA only costs tail time)
+        cap -= cap % CL;
+        if (a.n_groups > cap) {
+            cfg.gridDim = dim3(cap);
+            a.stagger_ns = stagger_override;   // spreading the cluster start times over a tile period measured neutral: off by default
+        }
     }
+    prof_begin(e, kc);
+    CU((cudaLaunchKernelEx(&cfg, post_attn_kernel<C, NT, UU, CL, PERSIST>, a)));
     prof_end(e);
     CU(cudaGetLastError());
     return MG_OK;
@@ -315,11 +326,19 @@ static int launch_post_attn(mg_engine *e, int C, const PostAttnArgs &a, int MT, 
     static const int u_override = getenv("MAPF_GPT_B200_POST_U") ? atoi(getenv("MAPF_GPT_B200_POST_U")) : 0;
     const bool pair = cl_req == 2 && MT % 2 == 0 && a.wstream_pair != nullptr;
     if (C == 160 && u_override == 1) return launch_post_attn_c<160, 1, 1>(e, a, MT, kc);
+    // Persistent CTAs (tile loop inside the kernel) for the layers that emit the next block's q/k/v: default where one CTA fits
+    // per SM (C = 256: +6 % on the kernel), opt-in where two do (C = 160: -3 %).  MAPF_GPT_B200_POST_PERSIST=0/1 overrides.
+    static const int persist_req = getenv("MAPF_GPT_B200_POST_PERSIST") ? atoi(getenv("MAPF_GPT_B200_POST_PERSIST")) : -1;
+    const bool persist = a.qkv_out != nullptr && pair && (persist_req >= 0 ? persist_req == 1 : C == 256);
     if (C == 160) {
         if (nt_override == 2 && !single_tiles && MT % 2 == 0) return launch_post_attn_c<160, 2>(e, a, MT, kc);
+        if (persist) return launch_post_attn_c<160, 1, 0, 2, true>(e, a, MT, kc);
         return pair ? launch_post_attn_c<160, 1, 0, 2>(e, a, MT, kc) : launch_post_attn_c<160, 1>(e, a, MT, kc);
     }
-    if (C == 256) return pair ? launch_post_attn_c<256, 1, 0, 2>(e, a, MT, kc) : launch_post_attn_c<256, 1>(e, a, MT, kc);
+    if (C == 256) {
+        if (persist) return launch_post_attn_c<256, 1, 0, 2, true>(e, a, MT, kc);
+        return pair ? launch_post_attn_c<256, 1, 0, 2>(e, a, MT, kc) : launch_post_attn_c<256, 1>(e, a, MT, kc);
+    }
     return fail(MG_ERR_ARG, "post_attn: unsupported width %d", C);
 }
 
@@ -492,9 +511,10 @@ static int ensure_workspace(mg_engine *e, int want_seqs)
     const int C = e->model.cfg.n_embd;
     int chunk = std::min(want_seqs, 8192);
     if (chunk <= w.chunk_seqs) return MG_OK;
-    cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc);
-    w.X = w.Xc = nullptr; w.XN = w.QKV = w.ATT = w.HID = w.ATTc = nullptr; w.chunk_seqs = 0;
+    cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
+    w.X = w.Xc = w.STATS = nullptr; w.XN = w.QKV = w.ATT = w.HID = w.ATTc = nullptr; w.chunk_seqs = 0;
     const size_t M = (size_t)chunk * 256;
+    if (e->model.ln_fused) CU(dalloc(&w.STATS, M * 2 * (C / 128)));
     CU(dalloc(&w.X, M * C));
     CU(dalloc(&w.XN, M * C));
     CU(dalloc(&w.QKV, M * 3 * C));
@@ -642,16 +662,20 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             prof_end(e);
             continue;
         }
+        const bool lnf = m.ln_fused;    // ln_1 / ln_2 live in the epilogues of the GEMMs around them; w.XN holds the RAW bf16 residual
         prof_begin(e, KC_EMBED);
-        embed_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, C);
+        embed_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, C, lnf ? w.XN : nullptr, w.STATS);
         prof_end(e);
         for (int l = 0; l < m.cfg.n_layer; l++) {
             const Layer &L = m.layers[l];
-            prof_begin(e, KC_LN);
-            launch_ln(e, w.X, L.ln1, w.XN, C, MT);
-            prof_end(e);
+            if (!lnf) {
+                prof_begin(e, KC_LN);
+                launch_ln(e, w.X, L.ln1, w.XN, C, MT);
+                prof_end(e);
+            }
             GemmArgs g{};
             g.A = w.XN; g.W = L.wqkv; g.Wp = L.wqkv_p; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
+            if (lnf) { g.stats_in = w.STATS; g.colsum = L.cs_qkv; }
             if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
             AttnArgs at{};
             at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
@@ -659,15 +683,20 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             if ((rc = launch_attn(e, at, hs, ns, e->stream, !e->safe_softmax))) return rc;
             g = GemmArgs{};
             g.A = w.ATT; g.W = L.wproj; g.Wp = L.wproj_p; g.out = w.X; g.M = M; g.N = C; g.K = C;
+            if (lnf) { g.xb_out = w.XN; g.stats_out = w.STATS; }                       // operand + statistics of ln_2
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ))) return rc;
-            prof_begin(e, KC_LN);
-            launch_ln(e, w.X, L.ln2, w.XN, C, MT);
-            prof_end(e);
+            if (!lnf) {
+                prof_begin(e, KC_LN);
+                launch_ln(e, w.X, L.ln2, w.XN, C, MT);
+                prof_end(e);
+            }
             g = GemmArgs{};
             g.A = w.XN; g.W = L.wfc; g.Wp = L.wfc_p; g.out = w.HID; g.M = M; g.N = 4 * C; g.K = C;
+            if (lnf) { g.stats_in = w.STATS; g.colsum = L.cs_fc; }
             if ((rc = launch_gemm<EPI_GELU>(e, m.BN, g, KC_FC))) return rc;
             g = GemmArgs{};
             g.A = w.HID; g.W = L.wproj2; g.Wp = L.wproj2_p; g.out = w.X; g.M = M; g.N = C; g.K = 4 * C;
+            if (lnf && l + 1 < m.cfg.n_layer) { g.xb_out = w.XN; g.stats_out = w.STATS; }   // ... of the next block's ln_1
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ2))) return rc;
         }
         prof_begin(e, KC_HEAD);
@@ -1072,10 +1101,10 @@ void mg_engine_destroy(mg_engine *e)
     Model &m = e->model;
     cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti); cudaFree(m.tab0);
     for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); cudaFree(L.wstream_pair);
-                                cudaFree(L.wqkv_p); cudaFree(L.wproj_p); cudaFree(L.wfc_p); cudaFree(L.wproj2_p); }
+                                cudaFree(L.wqkv_p); cudaFree(L.wproj_p); cudaFree(L.wfc_p); cudaFree(L.wproj2_p); cudaFree(L.cs_qkv); cudaFree(L.cs_fc); }
     Workspace &w = e->ws;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
-    cudaFree(w.Xc); cudaFree(w.ATTc);
+    cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
     for (auto &p : e->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
@@ -1139,6 +1168,25 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         e->prune_last = !(np && np[0] == '1');
     }
     const bool pair_gemm = !m.fused && BN == 256 && !(getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0');
+    // LayerNorm folded into the CTA-pair GEMMs (no LayerNorm kernel, no normalised copy of the residual in HBM): needs every GEMM
+    // of the block on the pair kernel.  MAPF_GPT_B200_LN_FUSED=0 keeps the separate one-pass LayerNorm kernel (A/B, fallback).
+    m.ln_fused = pair_gemm && C % 128 == 0 && !(getenv("MAPF_GPT_B200_LN_FUSED") && getenv("MAPF_GPT_B200_LN_FUSED")[0] == '0');
+    auto bf_round = [](float f) { const uint32_t u = (uint32_t)f2bf(f) << 16; float r; memcpy(&r, &u, 4); return r; };
+    // rows of W (N x K) scaled per column by the LayerNorm gain; returns the column sums of the bf16-ROUNDED result (what the
+    // tensor core multiplies), so that rstd * (x W^T - mean * colsum) is exact for a constant row
+    auto fold_gain = [&](std::vector<float> &W, int N, int K, const float *gain, float **cs_dev) -> int {
+        std::vector<float> cs((size_t)N);
+        for (int n = 0; n < N; n++) {
+            double acc = 0.0;
+            for (int k = 0; k < K; k++) {
+                float &v = W[(size_t)n * K + k];
+                v *= gain[k];
+                acc += (double)bf_round(v);
+            }
+            cs[n] = (float)acc;
+        }
+        return upload_f32(cs.data(), cs.size(), cs_dev);
+    };
     // attention scale folded into Wq: q' = (log2(e) / sqrt(hs)) q, so S = Q' K^T is already the exponent of 2 (gpt_kernels.cuh,
     // "max-free softmax"); the fold happens in fp32, before the one bf16 rounding of the weight
     m.q_fold = (float)(1.4426950408889634 / std::sqrt((double)hs));
@@ -1148,6 +1196,7 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         w += C;
         for (size_t i = 0; i < 3 * CC; i++) wq_s[i] = i < CC ? w[i] * m.q_fold : w[i];
         if ((rc = upload_packed(wq_s.data(), 3 * C, C, BN, &L.wqkv))) return rc;
+        if (m.ln_fused && (rc = fold_gain(wq_s, 3 * C, C, w - C, &L.cs_qkv))) return rc;     // w - C: this block's ln_1 gain
         if (pair_gemm && (rc = upload_packed_pair(wq_s.data(), 3 * C, C, BN, &L.wqkv_p))) return rc;
         w += 3 * CC;
         const float *wproj = w;
@@ -1159,7 +1208,11 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
         w += C;
         const float *wfc = w;
         if ((rc = upload_packed(w, 4 * C, C, BN, &L.wfc))) return rc;
-        if (pair_gemm && (rc = upload_packed_pair(w, 4 * C, C, BN, &L.wfc_p))) return rc;
+        if (m.ln_fused) {   // ln_2's gain folded into the c_fc columns of the pair packing
+            std::vector<float> wfc_s(w, w + 4 * CC);
+            if ((rc = fold_gain(wfc_s, 4 * C, C, g2, &L.cs_fc))) return rc;
+            if ((rc = upload_packed_pair(wfc_s.data(), 4 * C, C, BN, &L.wfc_p))) return rc;
+        } else if (pair_gemm && (rc = upload_packed_pair(w, 4 * C, C, BN, &L.wfc_p))) return rc;
         w += 4 * CC;
         const float *wproj2 = w;
         if ((rc = upload_packed(w, C, 4 * C, BN, &L.wproj2))) return rc;

@@ -40,12 +40,18 @@ struct PostAttnArgs {
     const uint8_t *tokens0;        // [MT * 128] token ids of this chunk
     const uint4 *tab0;             // [67][256][tab_nrec] records, x first
     int tab_nrec;
+    // tile groups (of NT tiles) in this launch.  A CTA processes groups blockIdx.x, blockIdx.x + gridDim.x, ...: with
+    // gridDim.x == n_groups every CTA owns one group; the persistent launch (fused-QKV layers) sizes the grid to the resident
+    // CTAs and keeps barriers, TMEM and the weight ring alive across tiles.
+    int n_groups;
+    int stagger_ns;                // persistent launch: start offsets of the clusters are spread over this many ns (0 = none)
 };
-// steady-state CTAs (not the first wave, whose loads all hit DRAM at once); single-tile launches have fewer CTAs and stamp nothing
+// steady-state tile groups (not the first wave, whose loads all hit DRAM at once), keyed by the group index `mg_group` in scope;
+// single-tile launches have fewer groups and stamp nothing
 #define MG_STAMP_CTA0 2048u
 #define MG_STAMP(id)                                                                     \
     do {                                                                                 \
-        if (a.timeline != nullptr && (blockIdx.x - MG_STAMP_CTA0) < 4u) a.timeline[(blockIdx.x - MG_STAMP_CTA0) * 128 + (id)] = clock64(); \
+        if (a.timeline != nullptr && (mg_group - MG_STAMP_CTA0) < 4u) a.timeline[(mg_group - MG_STAMP_CTA0) * 128 + (id)] = clock64(); \
     } while (0)
 
 // Phase profile (builds with -DMG_PHASE_PROF only, tools/phase_profile.py): cycles per phase summed over ALL CTAs of every
@@ -161,7 +167,14 @@ struct PostAttnCfg {
 //   * workers of both CTAs arrive (one elected lane per warp) on the LEADER's barriers; the leader's commits are multicast
 //     to the barriers of both CTAs;
 //   * the peer's otherwise idle UMMA warp relays "my half of stage i landed" (and "my att tile landed") to the leader.
-template <int C, int NT, int UU = 0, int CL = 1>
+// PERSIST: the CTA loops over tile groups blockIdx.x, blockIdx.x + gridDim.x, ... (barriers, TMEM, weight ring and the issuer's
+// descriptors live across tiles; the next att tile is requested as soon as the A buffer is free, the next residual tile is
+// prefetched into L2).  !PERSIST: one group per CTA, and the residual tile is requested BEFORE the rendezvous (inside a tile loop
+// the compiler parks those 80 registers in local memory across the rendezvous -- a store that waits for the data).
+// Measured (profiles/r02_post_attn_persistent.md): PERSIST wins where one CTA fits per SM (C = 256: 3.89 -> 3.65 ms per launch)
+// and loses where two do (C = 160: 1.92 -> 1.98 ms; two co-resident CTAs started by the hardware at different times already
+// hide each other's launch gaps, while resident CTAs run in lockstep), so the launcher uses it for C = 256 only.
+template <int C, int NT, int UU = 0, int CL = 1, bool PERSIST = false>
 __global__ void __launch_bounds__(PostAttnCfg<C, NT, UU, CL>::THREADS, PostAttnCfg<C, NT, UU, CL>::CTAS_PER_SM)
 post_attn_kernel(const PostAttnArgs a)
 {
@@ -200,9 +213,26 @@ post_attn_kernel(const PostAttnArgs a)
     const bool fuse_qkv = a.qkv_out != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt0 = blockIdx.x * NT;
+    const int mt0 = blockIdx.x * NT;              // first tile of the CTA's first group
+    const int n_groups = a.n_groups, gstride = (int)gridDim.x;
+    uint32_t mg_group = blockIdx.x;               // group being processed (timeline stamps)
 
     const int n_stages = K::TOTAL_STAGES + (fuse_qkv ? K::QKV_STAGES : 0);
+    if (a.stagger_ns > 0) {
+        // Persistent launch: identical CTAs started together stay in lockstep, so every HBM phase (residual / att loads, x' and
+        // q/k/v stores) would be a device-wide burst with the memory system idle in between (measured: 8.5k cycles per tile
+        // waiting for the residual).  Each cluster therefore starts at its own offset inside one tile period (golden-ratio
+        // sequence over the cluster index); tiles take equal time, so the offsets persist for the whole launch.
+        const uint32_t cid = blockIdx.x / CL;
+        const uint32_t frac = (cid * 0x9E3779B1u) >> 16;                      // [0, 65536)
+        const long long wait_ns = ((long long)a.stagger_ns * frac) >> 16;
+        long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(256);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < wait_ns);
+    }
     if (warp == PROD_WARP && lane == 0) {
         // the producer owns the barriers of its copies and starts them before the CTA-wide (and cluster-wide) rendezvous:
         // the att tile and the first S weight stages are in flight while TMEM is being allocated
@@ -224,11 +254,10 @@ post_attn_kernel(const PostAttnArgs a)
             bulk_g2s(ring + i * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[i]);
         }
     }
-    // workers: the residual tile is on its way to registers meanwhile (it goes into the TMEM accumulator after the rendezvous)
     constexpr int HALF = C / 2;                           // residual columns handled by one worker thread
-    float4 xv[HALF / 4];
-    if (warp < 8 * NT) {
-        const int mtl = mt0 + (warp >> 3), row = (warp & 3) * 32 + lane, hh = (warp >> 2) & 1;
+    float4 xv[HALF / 4];                                  // this thread's residual columns
+    auto load_x = [&](int mtl) {
+        const int row = (warp & 3) * 32 + lane, hh = (warp >> 2) & 1;
         if (a.tab0 != nullptr) {   // block 0: this thread's 2C contiguous bytes of its token's record (L2-resident table)
             const int tok = min((int)a.tokens0[(size_t)mtl * 128 + row], 66);
             const float4 *src = reinterpret_cast<const float4 *>(a.tab0 + ((size_t)tok * 256 + ((mtl & 1) << 7) + row) * a.tab_nrec) + hh * (HALF / 4);
@@ -239,6 +268,9 @@ post_attn_kernel(const PostAttnArgs a)
 #pragma unroll
             for (int j = 0; j < HALF / 4; j++) xv[j] = Xl[(size_t)(hh * (HALF / 4) + j) * 128];
         }
+    };
+    if constexpr (!PERSIST) {   // the residual tile is on its way to registers during the rendezvous
+        if (warp < 8 * NT) load_x(mt0 + (warp >> 3));
     }
     if (threadIdx.x == 0) {
         mbar_init(bar_proj, 1);
@@ -296,23 +328,46 @@ post_attn_kernel(const PostAttnArgs a)
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             const uint8_t *src = reinterpret_cast<const uint8_t *>(a.wstream);
-            for (int i = S; i < n_stages; i++) {
-                const int s = i % S;
-                mbar_wait(&empty[s], ((i / S) & 1) ^ 1);
-                mbar_expect_tx(&full[s], K::SLOT_BYTES);
-                bulk_g2s(ring + s * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[s]);
+            int gi = S < n_stages ? S : n_stages;          // ring cursor over ALL tiles of this CTA (the first S stages are in flight)
+            int it = 0;
+            for (int g = blockIdx.x; g < n_groups; g += gstride, it++) {
+                if (it > 0) {
+                    // the A tile buffer is free once the previous tile's last c_attn UMMAs (half-tile 5 = second use of
+                    // accumulator buffer 2 in that tile) have retired: wait for both of that tile's completions in order
+                    for (int t = 0; t < NT; t++) {
+                        mbar_wait(&bar_qf[t * 3 + 2], 0);
+                        mbar_wait(&bar_qf[t * 3 + 2], 1);
+                    }
+                    for (int t = 0; t < NT; t++) {
+                        mbar_expect_tx(&bar_att[t], K::A_BYTES);
+                        bulk_g2s(As + t * K::A_BYTES, a.att + (size_t)(g * NT + t) * C * 128, K::A_BYTES, &bar_att[t]);
+                    }
+                }
+                if (g + gstride < n_groups && a.tab0 == nullptr)   // the next tile's residual: on its way into L2 during this tile
+                    bulk_prefetch_l2(a.x + (size_t)(g + gstride) * NT * C * 128, NT * C * 128 * 4);
+                for (int i = it == 0 ? gi : 0; i < n_stages; i++, gi++) {
+                    const int s = gi % S;
+                    mbar_wait(&empty[s], ((gi / S) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], K::SLOT_BYTES);
+                    bulk_g2s(ring + s * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[s]);
+                }
+                if constexpr (!PERSIST) break;
             }
         }
     } else if (warp == MMA_WARP && PAIR && !leader) {
         // ------------------------------------------------------------------ peer of a CTA pair: relay "landed" to the leader
-        mbar_wait(&bar_att[0], 0);
-        if (lane == 0) mbar_arrive_cluster(&bar_x[0], 0);
-        __syncwarp();
-        for (int i = 0; i < n_stages; i++) {
-            const int s = i % S;
-            mbar_wait(&full[s], (i / S) & 1);
-            if (lane == 0) mbar_arrive_cluster(&pfull[s], 0);
+        int gi = 0, it = 0;
+        for (int g = blockIdx.x; g < n_groups; g += gstride, it++) {
+            mbar_wait(&bar_att[0], it & 1);
+            if (lane == 0) mbar_arrive_cluster(&bar_x[0], 0);
             __syncwarp();
+            for (int i = 0; i < n_stages; i++, gi++) {
+                const int s = gi % S;
+                mbar_wait(&full[s], (gi / S) & 1);
+                if (lane == 0) mbar_arrive_cluster(&pfull[s], 0);
+                __syncwarp();
+            }
+            if constexpr (!PERSIST) break;
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ UMMA issuer
@@ -323,7 +378,8 @@ post_attn_kernel(const PostAttnArgs a)
             constexpr uint32_t idescC = umma_idesc_bf16(UM, C, 0, 0);
             constexpr uint32_t idescH = umma_idesc_bf16(UM, HC, 0, 0);
             const uint32_t a_addr = smem_u32(As), h_addr = smem_u32(Hs), r_addr = smem_u32(ring);
-            int i = 0;  // stage cursor
+            int i = 0;  // ring cursor over ALL tiles of this CTA
+            int it = 0;
             MG_LAP_INIT;
             auto stage_wait = [&](int idx) -> uint32_t {
                 const int s = idx % S;
@@ -334,12 +390,15 @@ post_attn_kernel(const PostAttnArgs a)
                 if (lane == 0) MG_LAP(20);                   // waiting for the weight ring
                 return r_addr + s * K::SLOT_BYTES;
             };
+            for (int g = blockIdx.x; g < n_groups; g += gstride, it++) {
+            mg_group = g;
+            const uint32_t ph = it & 1;                      // parity of the barriers that complete once per tile
             // proj: acc_main (pre-loaded with x) += att @ Wproj^T
             if (elect_one()) MG_STAMP(0);
             __syncwarp();
             for (int t = 0; t < NT; t++) {
-                mbar_wait(&bar_att[t], 0);
-                mbar_wait(&bar_x[t], 0);
+                mbar_wait(&bar_att[t], ph);
+                mbar_wait(&bar_x[t], ph);
             }
             tc_fence_after();
             if (lane == 0) MG_LAP(22);                       // att tile + residual pre-load
@@ -368,7 +427,7 @@ post_attn_kernel(const PostAttnArgs a)
 #pragma unroll
                     for (int t = 0; t < NT; t++) {
                         if (st == 0) {
-                            if (j == 0) mbar_wait(&bar_ln2[t], 0);
+                            if (j == 0) mbar_wait(&bar_ln2[t], ph);
                             else mbar_wait(&bar_a1e[t], (j - 1) & 1);
                             tc_fence_after();
                         }
@@ -427,7 +486,7 @@ post_attn_kernel(const PostAttnArgs a)
                 // next block's c_attn: [q|k|v] = LN1_next(x') @ Wqkv^T as six HC-wide half n-tiles rotating through three
                 // accumulator buffers (the FC accumulator and the two halves of the main one, all free by now), so the
                 // UMMAs of half-tile h+1 run while the workers drain half-tile h
-                for (int t = 0; t < NT; t++) mbar_wait(&bar_qa[t], 0);
+                for (int t = 0; t < NT; t++) mbar_wait(&bar_qa[t], ph);
                 tc_fence_after();
                 for (int hh = 0; hh < 6; hh++) {
                     const int buf = hh % 3;
@@ -459,6 +518,8 @@ post_attn_kernel(const PostAttnArgs a)
                 if (elect_one()) MG_STAMP(41);
                 __syncwarp();
             }
+            if constexpr (!PERSIST) break;
+            }   // tile groups
             if (lane == 0) MG_LAP(21);
         }
     } else {
@@ -466,19 +527,25 @@ post_attn_kernel(const PostAttnArgs a)
         const int t = warp >> 3;                          // tile of this worker
         const int q = warp & 3, h = (warp >> 2) & 1;
         const int r = q * 32 + lane;
-        const int mt = mt0 + t;
         const uint32_t trow = tmem + t * K::TILE_COLS + ((uint32_t)(q * 32) << 16);
         uint8_t *At = As + t * K::A_BYTES;
         float *red_s = red + t * 512, *red_q = red_s + 256;
         const float inv_c = 1.0f / (float)C;
         const uint32_t nb = 1 + t;                        // named barrier of this tile's 256 workers
-        float4 *Xg = reinterpret_cast<float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
         MG_LAP_INIT;
 #define MG_WLAP(id) do { if (threadIdx.x == 0) MG_LAP(id); } while (0)
+        int it = 0;
+#pragma unroll 1
+        for (int g = blockIdx.x; g < n_groups; g += gstride, it++) {
+        mg_group = g;
+        const uint32_t ph = it & 1;                       // parity of the barriers that complete once per tile
+        const int mt = g * NT + t;
+        float4 *Xg = reinterpret_cast<float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
 
         // ---- x -> TMEM accumulator (overlaps the att tile load); c_proj then accumulates onto it.
         // All loads are issued before the first TMEM store so the thread pays ONE memory round trip.
         {
+            if constexpr (PERSIST) load_x(mt);            // all loads in flight, then the stores (L2 prefetch sent a tile ago)
 #pragma unroll
             for (int i = 0; i < HALF / 16; i++) {
                 uint32_t v[16];
@@ -496,7 +563,7 @@ post_attn_kernel(const PostAttnArgs a)
         MG_WLAP(0);      // residual tile -> TMEM
 
         // ---- epilogue 1: LN2(x1) -> A tile (x1 = x + proj stays in TMEM)
-        mbar_wait(bar_proj, 0);
+        mbar_wait(bar_proj, ph);
         tc_fence_after();
         MG_WLAP(1);      // waiting for att tile + c_proj
         if (threadIdx.x == 0) MG_STAMP(50);
@@ -586,7 +653,7 @@ post_attn_kernel(const PostAttnArgs a)
         }
 
         // ---- final epilogue: x' -> HBM, xn = LN1_next(x') -> HBM
-        mbar_wait(bar_done, 0);
+        mbar_wait(bar_done, ph);
         tc_fence_after();
         MG_WLAP(8);      // waiting for the last proj2
         if (threadIdx.x == 0) MG_STAMP(90);
@@ -687,7 +754,14 @@ post_attn_kernel(const PostAttnArgs a)
                 MG_WLAP(12);  // q/k/v half-tile -> HBM
             }
         }
+        // the next tile's residual goes into accumulator columns that OTHER workers of this tile have just drained
+        if constexpr (!PERSIST) {
+            MG_WLAP(13);
+            break;
+        }
+        if (g + gstride < n_groups) named_bar_sync(nb, 256);
         MG_WLAP(13);
+        }   // tile groups
     }
     if (threadIdx.x == 0) MG_STAMP(91);
     tc_fence_before();

@@ -24,16 +24,73 @@ struct GemmArgs {
     int M, N, K;             // M % 128 == 0, N % BN == 0, K % BK == 0
     int C, n_head, hs;       // EPI_QKV only
     int dbg_swap_lbo_sbo;    // test hook: swap descriptor fields (layout bring-up)
+    // LayerNorm folded into the GEMMs around it (gemm_pair_persistent_kernel only; DESIGN.md "85M: LayerNorm without a pass
+    // of its own").  The residual GEMM (EPI_RESID) also writes the updated residual as a bf16 tile image (xb_out, the next
+    // GEMM's A operand, NOT normalised) and per-row partial sums / sums of squares of its 128-column half tile (stats_out
+    // [M/128][N/128][2][128]).  The consumer (EPI_QKV / EPI_GELU, weights carrying the LayerNorm gain) multiplies the raw rows
+    // and applies  LN(x) W^T = rstd * (x W^T - mean * colsum(W))  in its epilogue (stats_in [M/128][K/128][2][128], colsum [N]).
+    __nv_bfloat16 *xb_out;
+    float *stats_out;
+    const float *stats_in;
+    const float *colsum;
 };
 
-// erf-GELU on a PAIR of values with packed fp32x2 math (FFMA2): erf(z) ~ z * P(z^2), odd degree-17 polynomial on
-// |z| <= 3, FMA-only, no MUFU.  Max |gelu error| 5e-5 over all x; the result is rounded to bf16 (rel. 4e-3) right after,
-// see DESIGN.md "Tolerance".  The MLP phase of post_attn_kernel is bound by the FP32 FMA pipe (an FFMA2 occupies it for two
-// cycles), so the form below minimises FMA-pipe work: the clamp runs on the ALU pipe (FMNMX), and 1/sqrt(2), the 1/2 of
-// gelu = x/2 * (1 + erf) and the powers of 2 of z^2 = x^2/2 are folded into the coefficients:
-//     gelu(x) = x * (0.5 + xc * Q(xc^2)),   xc = clamp(x, +-3*sqrt(2)),   Q_k = P_k / (2 sqrt(2) 2^k)
-// 11 FMA-pipe operations per element (was 14 with the saturating-FFMA clamp).
-#ifndef MG_GELU_V1
+// erf-GELU (model.py:80, nn.GELU() = x * Phi(x)) on a PAIR of values with packed fp32x2 math.  Three forms, one compiled in.
+// All evaluate the EXACT erf-based Phi through an odd polynomial u(x) = xc * (a + b xc^2 + c xc^4), xc = clamp(x, +-8), fitted
+// (minimax) to erf -- not the textbook tanh-GELU constants: max |gelu error| of the fit 2.6e-5 over all x.
+//
+//  default         x/2 * (1 + tanh(u)) with ONE MUFU.TANH per element: 6 FMA-pipe operations + 1 MUFU.  tanh.approx.f32 carries a
+//                  relative error of 2^-11 on tanh, i.e. up to 2.5e-4 |x| on the result -- an order of magnitude below the bf16
+//                  rounding (rel. 4e-3) applied right after; measured logit error unchanged (DESIGN.md "Tolerance").
+//  MG_GELU_LOGISTIC x / (1 + 2^(-2 log2(e) u)) with ex2.approx + rcp.approx (~1e-7 relative): same 6 FMA-pipe operations, 2 MUFU.
+//  MG_GELU_POLY    FMA-only: erf(z) ~ z * P(z^2), odd degree-17 polynomial on |z| <= 3, 11 FMA-pipe operations, no MUFU, max
+//                  |gelu error| 5e-5 (round 1's form).
+// The MLP phase of post_attn_kernel is bound by the FP32 FMA pipe (an FFMA2 occupies it for two cycles) while the MUFU unit
+// (16 results/clk/SM) idles: one MUFU per element balances the two pipes, two make MUFU the limit.  Measured per launch of
+// post_attn_kernel<160> / whole 2M step in one gpurun call: polynomial 1.84 ms / 722 k agent-steps/s, logistic 1.89 / 715 k,
+// tanh 1.78 / 740 k (6M: 227.6 k, 221 k, 231.6 k).
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#if defined(MG_GELU_LOGISTIC)
+__device__ __forceinline__ f32x2 gelu2(float x0, float x1)
+{
+    const float c0 = fminf(fmaxf(x0, -8.0f), 8.0f), c1 = fminf(fmaxf(x1, -8.0f), 8.0f);   // ALU pipe
+    const f32x2 xc = pk2(c0, c1);
+    const f32x2 t = mul2(xc, xc);
+    // -2 log2(e) * (0.7975078826 + 0.03700564737 t - 0.0003515169833 t^2)
+    f32x2 p = fma2(pk2(0.0010142636171501724f, 0.0010142636171501724f), t, pk2(-0.10677572789188232f, -0.10677572789188232f));
+    p = fma2(p, t, pk2(-2.3011213346411554f, -2.3011213346411554f));
+    float w0, w1;
+    upk2(mul2(p, xc), w0, w1);
+    const f32x2 d = add2(pk2(ex2_approx(w0), ex2_approx(w1)), pk2(1.0f, 1.0f));   // |w| <= 40: no overflow
+    float d0, d1, r0, r1;
+    upk2(d, d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    return mul2(pk2(x0, x1), pk2(r0, r1));
+}
+#elif !defined(MG_GELU_POLY) && !defined(MG_GELU_V1)   // default: MUFU.TANH
+__device__ __forceinline__ f32x2 gelu2(float x0, float x1)
+{
+    const float c0 = fminf(fmaxf(x0, -8.0f), 8.0f), c1 = fminf(fmaxf(x1, -8.0f), 8.0f);
+    const f32x2 xc = pk2(c0, c1);
+    const f32x2 t = mul2(xc, xc);
+    f32x2 p = fma2(pk2(-3.515169833e-4f, -3.515169833e-4f), t, pk2(0.03700564737f, 0.03700564737f));
+    p = fma2(p, t, pk2(0.7975078826f, 0.7975078826f));
+    float u0, u1;
+    upk2(mul2(p, xc), u0, u1);
+    float t0, t1;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+    const f32x2 hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
+    return fma2(hx, pk2(t0, t1), hx);
+}
+#elif !defined(MG_GELU_V1)   // MG_GELU_POLY
 __device__ __forceinline__ f32x2 gelu2(float x0, float x1)
 {
     constexpr float L = 4.2426406871192851f;
@@ -239,6 +296,9 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
 #pragma unroll
         for (int j = 0; j < 8; j++) xa[j] = X[(size_t)j * 128];          // first chunk: on its way while the UMMAs run
         wait_acc();
+        const bool ln_out = a.xb_out != nullptr;
+        uint4 *XB = reinterpret_cast<uint4 *>(a.xb_out) + ((size_t)mt * (a.N / 8) + nbase / 8) * 128 + r;
+        f32x2 s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
         auto chunk = [&](int c0, float4 (&x)[8], float4 (&xn)[8]) {
             if (c0 + 32 < HALF) {
 #pragma unroll
@@ -256,13 +316,55 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
                 x[j].w += __uint_as_float(v[4 * j + 3]);
                 X[(size_t)(c0 / 4 + j) * 128] = x[j];
             }
+            if (ln_out) {   // the new residual as the next GEMM's bf16 operand + this half tile's share of the row statistics
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const f32x2 e0 = pk2(x[j].x, x[j].y), e1 = pk2(x[j].z, x[j].w);
+                    s2 = add2(s2, add2(e0, e1));
+                    q2 = fma2(e0, e0, q2);
+                    q2 = fma2(e1, e1, q2);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    uint4 o;
+                    o.x = pack_bf16x2(x[2 * g].x, x[2 * g].y);
+                    o.y = pack_bf16x2(x[2 * g].z, x[2 * g].w);
+                    o.z = pack_bf16x2(x[2 * g + 1].x, x[2 * g + 1].y);
+                    o.w = pack_bf16x2(x[2 * g + 1].z, x[2 * g + 1].w);
+                    XB[(size_t)(c0 / 8 + g) * 128] = o;
+                }
+            }
         };
 #pragma unroll 1
         for (int c0 = 0; c0 < HALF; c0 += 64) {
             chunk(c0, xa, xb);
             chunk(c0 + 32, xb, xa);
         }
+        if (ln_out) {
+            float s0, s1, q0, q1;
+            upk2(s2, s0, s1);
+            upk2(q2, q0, q1);
+            float *S = a.stats_out + (((size_t)mt * (a.N / HALF) + nbase / HALF) * 2) * 128 + r;
+            S[0] = s0 + s1;
+            S[128] = q0 + q1;
+        }
     } else {
+        // LayerNorm of the A rows applied here (see GemmArgs): row statistics = fixed-order sum of the K/128 partials
+        float rstd = 1.f, nmr = 0.f;
+        const bool ln_in = (EPI == EPI_QKV || EPI == EPI_GELU) && a.stats_in != nullptr;
+        if (ln_in) {
+            const int np = a.K / 128;
+            const float *S = a.stats_in + ((size_t)mt * np * 2) * 128 + r;
+            float sum = 0.f, sq = 0.f;
+            for (int p = 0; p < np; p++) {
+                sum += S[(size_t)(2 * p) * 128];
+                sq += S[(size_t)(2 * p + 1) * 128];
+            }
+            const float mean = sum / (float)a.K;
+            const float var = fmaxf(sq / (float)a.K - mean * mean, 0.f);
+            rstd = rsqrtf(var + 1e-5f);
+            nmr = -mean * rstd;
+        }
         wait_acc();
 #pragma unroll 1
         for (int c0 = 0; c0 < HALF; c0 += 32) {
@@ -271,6 +373,17 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
             tmem_wait_ld();
             if (c0 + 32 >= HALF) drained();
             const int n0 = nbase + c0;
+            if (ln_in) {
+                const float4 *cs = reinterpret_cast<const float4 *>(a.colsum + n0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 c = __ldg(cs + j);
+                    v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), rstd, nmr * c.x));
+                    v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr * c.y));
+                    v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr * c.z));
+                    v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr * c.w));
+                }
+            }
             if constexpr (EPI == EPI_STORE_F32) {
                 float *C = reinterpret_cast<float *>(a.out) + (size_t)(mt * 128 + r) * a.N + n0;
 #pragma unroll
@@ -469,13 +582,6 @@ struct AttnArgs {
     do {                                                                                 \
         if (a.timeline != nullptr && blockIdx.x < 4) a.timeline[blockIdx.x * 128 + (id)] = clock64(); \
     } while (0)
-
-__device__ __forceinline__ float ex2_approx(float x)
-{
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 // 2^x for a PAIR of non-positive inputs on the FMA/ALU pipes instead of MUFU (the softmax is MUFU-bound: 16 ex2/clk/SM).
 // Cody-Waite: n = round(x) via the 1.5*2^23 magic add, f = x - n in [-0.5, 0.5], degree-3 polynomial for 2^f (max rel.
@@ -1205,20 +1311,49 @@ constexpr int attn_smem_bytes() { return 128 * HS * 2 + 256 * HS * 2 + 256 * (HS
 // ---------------------------------------------------------------------------------------------
 // x = wte[tok] + wpe[pos]  (model.py:171-175)  -> X_ti
 __global__ void __launch_bounds__(128) embed_kernel(const uint8_t *__restrict__ tokens, const float *__restrict__ wte,
-                                                    const float *__restrict__ wpe, float *__restrict__ X, int C)
+                                                    const float *__restrict__ wpe, float *__restrict__ X, int C,
+                                                    __nv_bfloat16 *__restrict__ xb_out, float *__restrict__ stats_out)
 {
     const int mt = blockIdx.x, r = threadIdx.x;
     const size_t row = (size_t)mt * 128 + r;
-    const int tok = tokens[row];
+    const int tok = min((int)tokens[row], 66);
     const int pos = (int)(row & 255);
     const float4 *te = reinterpret_cast<const float4 *>(wte + (size_t)tok * C);
     const float4 *pe = reinterpret_cast<const float4 *>(wpe + (size_t)pos * C);
     float4 *Xo = reinterpret_cast<float4 *>(X) + (size_t)mt * (C / 4) * 128 + r;
-    // every lane walks its own two rows (16-byte reads that share L1 lines from one iteration to the next): keep 16 loads in flight
+    if (xb_out == nullptr) {
+        // every lane walks its own two rows (16-byte reads that share L1 lines from one iteration to the next): keep 16 loads in flight
 #pragma unroll 8
-    for (int c4 = 0; c4 < C / 4; c4++) {
-        const float4 t = __ldg(te + c4), p = __ldg(pe + c4);
-        Xo[(size_t)c4 * 128] = make_float4(t.x + p.x, t.y + p.y, t.z + p.z, t.w + p.w);
+        for (int c4 = 0; c4 < C / 4; c4++) {
+            const float4 t = __ldg(te + c4), p = __ldg(pe + c4);
+            Xo[(size_t)c4 * 128] = make_float4(t.x + p.x, t.y + p.y, t.z + p.z, t.w + p.w);
+        }
+        return;
+    }
+    // LayerNorm folded into the GEMMs (GemmArgs): also the raw bf16 operand image and the row statistics of block 0's ln_1
+    // (the whole row's sums go into partial slot 0, the other C/128 - 1 slots are zero)
+    uint4 *XB = reinterpret_cast<uint4 *>(xb_out) + (size_t)mt * (C / 8) * 128 + r;
+    float s = 0.f, q = 0.f;
+#pragma unroll 4
+    for (int c8 = 0; c8 < C / 8; c8++) {
+        const float4 t0 = __ldg(te + 2 * c8), p0 = __ldg(pe + 2 * c8), t1 = __ldg(te + 2 * c8 + 1), p1 = __ldg(pe + 2 * c8 + 1);
+        const float4 a = make_float4(t0.x + p0.x, t0.y + p0.y, t0.z + p0.z, t0.w + p0.w);
+        const float4 b = make_float4(t1.x + p1.x, t1.y + p1.y, t1.z + p1.z, t1.w + p1.w);
+        Xo[(size_t)(2 * c8) * 128] = a;
+        Xo[(size_t)(2 * c8 + 1) * 128] = b;
+        s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+        q += ((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) + ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w));
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+        XB[(size_t)c8 * 128] = o;
+    }
+    const int np = C / 128;
+    float *S = stats_out + ((size_t)mt * np * 2) * 128 + r;
+    S[0] = s;
+    S[128] = q;
+    for (int p = 1; p < np; p++) {
+        S[(size_t)(2 * p) * 128] = 0.f;
+        S[(size_t)(2 * p + 1) * 128] = 0.f;
     }
 }
 

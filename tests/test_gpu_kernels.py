@@ -247,8 +247,9 @@ def test_generic_path_kernel_variants_agree(dev, monkeypatch):
     sd = W.scale_weights(W.perturb_layernorm(W.random_init(cfg)), 3.0)
     toks = np.random.default_rng(9).integers(0, 67, (66, 256)).astype(np.int8)
     outs = {}
-    for name, env in (("default", {}), ("single_cta_gemm", {"MAPF_GPT_B200_GEMM_PAIR": "0"}), ("smem_p_attention", {"MAPF_GPT_B200_ATTN_CLASSIC": "1"})):
-        for k in ("MAPF_GPT_B200_GEMM_PAIR", "MAPF_GPT_B200_ATTN_CLASSIC"):
+    for name, env in (("default", {}), ("ln_kernel", {"MAPF_GPT_B200_LN_FUSED": "0"}), ("single_cta_gemm", {"MAPF_GPT_B200_GEMM_PAIR": "0"}),
+                      ("smem_p_attention", {"MAPF_GPT_B200_ATTN_CLASSIC": "1", "MAPF_GPT_B200_LN_FUSED": "0"})):
+        for k in ("MAPF_GPT_B200_GEMM_PAIR", "MAPF_GPT_B200_ATTN_CLASSIC", "MAPF_GPT_B200_LN_FUSED"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -256,11 +257,13 @@ def test_generic_path_kernel_variants_agree(dev, monkeypatch):
         eng.load_model(sd, cfg)
         outs[name] = eng.forward_tokens(toks)
         eng.close()
-    assert np.abs(outs["default"] - outs["single_cta_gemm"]).max() < 1e-3
-    assert np.abs(outs["default"] - outs["smem_p_attention"]).max() < 2e-2
+    # LayerNorm folded into the pair GEMMs (default) vs the LayerNorm kernel: the operand is bf16(x) instead of bf16(LN(x))
+    assert np.abs(outs["default"] - outs["ln_kernel"]).max() < 2e-2
+    assert np.abs(outs["ln_kernel"] - outs["single_cta_gemm"]).max() < 1e-3      # same arithmetic, different tiling
+    assert np.abs(outs["ln_kernel"] - outs["smem_p_attention"]).max() < 2e-2
     from oracle import gpt_oracle as G
     ref = G.forward_logits(sd, cfg.n_layer, cfg.n_head, torch.from_numpy(toks.astype(np.int64)))[:, :5].numpy()
-    assert np.abs(outs["default"] - ref).max() < LOGIT_TOL
+    assert np.abs(outs["default"] - ref).max() < LOGIT_TOL and np.abs(outs["ln_kernel"] - ref).max() < LOGIT_TOL
 
 
 # ------------------------------------------------------------------------------------------------ large maps
