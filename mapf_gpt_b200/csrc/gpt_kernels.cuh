@@ -373,15 +373,14 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
             tmem_wait_ld();
             if (c0 + 32 >= HALF) drained();
             const int n0 = nbase + c0;
-            if (ln_in) {
+            if (ln_in) {   // packed fp32x2: two FMA-pipe instructions per pair of outputs
                 const float4 *cs = reinterpret_cast<const float4 *>(a.colsum + n0);
+                const f32x2 rs2 = pk2(rstd, rstd), nm2 = pk2(nmr, nmr);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float4 c = __ldg(cs + j);
-                    v[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 0]), rstd, nmr * c.x));
-                    v[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr * c.y));
-                    v[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr * c.z));
-                    v[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr * c.w));
+                    upk2u(fma2(pk2u(v[4 * j + 0], v[4 * j + 1]), rs2, mul2(nm2, pk2(c.x, c.y))), v[4 * j + 0], v[4 * j + 1]);
+                    upk2u(fma2(pk2u(v[4 * j + 2], v[4 * j + 3]), rs2, mul2(nm2, pk2(c.z, c.w))), v[4 * j + 2], v[4 * j + 3]);
                 }
             }
             if constexpr (EPI == EPI_STORE_F32) {
@@ -1069,7 +1068,8 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * BUF_BYTES);
     uint64_t *full = bars, *empty = bars + 2, *bS = bars + 4, *bP = bars + 5, *bO = bars + 6, *bE = bars + 7;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    uint64_t *bS1 = bars + 8, *bP1 = bars + 9;   // FAST: second key half (keys 128..255) of S / P
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
     volatile int *item_of = reinterpret_cast<volatile int *>(tmem_slot + 1);   // [2] item held by each buffer, -1 = no more work
     // [2][128] row-max exchange in bf16: both halves of a row read the same two rounded values, and softmax does not care
     // which offset is subtracted -- fp32 here would put the CTA 80 bytes over the two-CTAs-per-SM shared-memory budget
@@ -1080,6 +1080,7 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
         mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
         mbar_init(bS, 1); mbar_init(bP, 256); mbar_init(bO, 1); mbar_init(bE, 256);
+        mbar_init(bS1, 1); mbar_init(bP1, 256);
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc<256>(tmem_slot);
@@ -1146,6 +1147,51 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
             for (int qt = 0; qt < 2; qt++, t++) {
                 if (t > 0) mbar_wait(bE, (t - 1) & 1);      // previous tile's O drained: the S columns are free
                 tc_fence_after();
+                if constexpr (FAST) {
+                    // Key halves pipelined against the softmax: S_lo and S_hi are separate N = 128 UMMAs with their own commits
+                    // (the workers start on keys 0..127 while S_hi is still being computed), and P_lo V_lo is issued as soon as
+                    // the first half of P is in TMEM, i.e. it runs while the workers exponentiate keys 128..255.
+                    // TMEM: S = [0,256); P_lo = [0,32) | [96,128), P_hi = [128,160) | [224,256) (each thread converts inside its own
+                    // 64 columns); [O | rowsum] = [32,80), inside the first half's columns, which are consumed by then.
+                    constexpr uint32_t idescSh = umma_idesc_bf16(128, 128, 0, 0);
+                    if (elect_one()) {
+                        if (k == 40) MG_ASTAMP(100 + 3 * qt);
+#pragma unroll
+                        for (int ks = 0; ks < HS / 16; ks++)
+                            umma_ss(tmem, umma_desc(qa + qt * 2048 + ks * 2 * 4096, 4096, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128),
+                                    idescSh, ks != 0 ? 1u : 0u);
+                        umma_commit(bS);
+#pragma unroll
+                        for (int ks = 0; ks < HS / 16; ks++)
+                            umma_ss(tmem + 128, umma_desc(qa + qt * 2048 + ks * 2 * 4096, 4096, 128),
+                                    umma_desc(ka + 2048 + ks * 2 * 4096, 4096, 128), idescSh, ks != 0 ? 1u : 0u);
+                        umma_commit(bS1);
+                    }
+                    __syncwarp();
+                    mbar_wait(bP, t & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (k == 40) MG_ASTAMP(101 + 3 * qt);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++)
+                            umma_ts(tmem + 32, tmem + (ks < 4 ? ks * 8 : 96 + (ks - 4) * 8), umma_desc(va + ks * 2 * 128, 128, 4096), idescO,
+                                    ks != 0 ? 1u : 0u);
+                    }
+                    __syncwarp();
+                    mbar_wait(bP1, t & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 8; ks < 16; ks++)
+                            umma_ts(tmem + 32, tmem + (ks < 12 ? 128 + (ks - 8) * 8 : 224 + (ks - 12) * 8), umma_desc(va + ks * 2 * 128, 128, 4096),
+                                    idescO, 1u);
+                        umma_commit(bO);
+                        if (k == 40) MG_ASTAMP(102 + 3 * qt);
+                        if (qt == 1) umma_commit(&empty[b]);   // all UMMAs reading this buffer have retired -> the producer may refill it
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (elect_one()) {
                     if (k == 40) MG_ASTAMP(100 + 3 * qt);
 #pragma unroll
@@ -1189,21 +1235,28 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 tc_fence_after();
                 if (stamp) MG_ASTAMP(110 + 8 * qt);
                 if constexpr (FAST) {
-                    // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S; 64 columns per TMEM round trip
+                    // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S.  All 8 warps take key half 0 first
+                    // (the thread pair of a row splits its 128 keys 64 / 64), then half 1: P_lo V_lo runs on the tensor pipe meanwhile.
                     f32x2 unused = pk2(0.f, 0.f);
 #pragma unroll 1
-                    for (int cb = 0; cb < 2; cb++) {
+                    for (int hf = 0; hf < 2; hf++) {
+                        if (hf == 1) {
+                            mbar_wait(bS1, t & 1);
+                            tc_fence_after();
+                        }
                         uint32_t v[64], w[32];
-                        tmem_ld32(trow + kh * 128 + cb * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                        tmem_ld32(trow + kh * 128 + cb * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                        const uint32_t sc0 = trow + hf * 128 + kh * 64;
+                        tmem_ld32(sc0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                        tmem_ld32(sc0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                         tmem_wait_ld();
                         exp2_pack_fast<64, false>(v, w, unused);
-                        tmem_st16(trow + kh * 128 + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
-                        tmem_st16(trow + kh * 128 + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
+                        const uint32_t pc0 = trow + hf * 128 + kh * 96;     // own columns: [0,32) for kh 0, [96,128) for kh 1
+                        tmem_st16(pc0, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
+                        tmem_st16(pc0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(hf == 0 ? bP : bP1);
                     }
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(bP);
                     if (stamp) MG_ASTAMP(113 + 8 * qt);
                 } else {
                 float mx = -INFINITY;
@@ -1254,8 +1307,9 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 tc_fence_after();
                 if (stamp) MG_ASTAMP(114 + 8 * qt);
                 uint32_t sv[8], v[16];
-                tmem_ld8(trow + 64 + HS, sv);            // row sum
-                tmem_ld16(trow + 64 + kh * 16, v);       // 16 of the 32 output columns
+                constexpr uint32_t OC = FAST ? 32 : 64;  // first column of [O | rowsum]
+                tmem_ld8(trow + OC + HS, sv);            // row sum
+                tmem_ld16(trow + OC + kh * 16, v);       // 16 of the 32 output columns
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(bE);
@@ -1297,7 +1351,7 @@ done:
     }
     if (warp == 9) tmem_dealloc<256>(tmem);
 }
-constexpr int attn_persistent_smem_bytes() { return 2 * (256 * 32 * 2 * 2 + 256 * 48 * 2) + 8 * 8 + 16 + 512; }
+constexpr int attn_persistent_smem_bytes() { return 2 * (256 * 32 * 2 * 2 + 256 * 48 * 2) + 10 * 8 + 16 + 512; }
 static_assert(2 * (attn_persistent_smem_bytes() + 1024) <= 233472, "two persistent attention CTAs must fit one SM");
 
 // (A one-CTA-per-SM variant with all 16 softmax warps on one query tile and two S tiles in TMEM was measured SLOWER than two

@@ -258,7 +258,8 @@ def test_generic_path_kernel_variants_agree(dev, monkeypatch):
         outs[name] = eng.forward_tokens(toks)
         eng.close()
     # LayerNorm folded into the pair GEMMs (default) vs the LayerNorm kernel: the operand is bf16(x) instead of bf16(LN(x))
-    assert np.abs(outs["default"] - outs["ln_kernel"]).max() < 2e-2
+    # (two independent bf16 roundings, each within LOGIT_TOL of the oracle below: their distance may reach twice that)
+    assert np.abs(outs["default"] - outs["ln_kernel"]).max() < 2 * LOGIT_TOL
     assert np.abs(outs["ln_kernel"] - outs["single_cta_gemm"]).max() < 1e-3      # same arithmetic, different tiling
     assert np.abs(outs["ln_kernel"] - outs["smem_p_attention"]).max() < 2e-2
     from oracle import gpt_oracle as G
