@@ -435,7 +435,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"), timeout=datetime.timedelta(seconds=240))
 
     head = run_config(args.model, args.map, args.agents, args.envs, args.steps, args.warmup, rank, world, local_rank,
                       do_e2e=not args.no_e2e)

@@ -238,18 +238,20 @@ class MAPFGPTInference:
         if self._tok_engine is None:
             self._tok_engine = RolloutEngine(1, 1, 11, 11, device=self._dev)
             self._tok_engine.load_model(self._sd, self._gpt_cfg)
-        logits = self._tok_engine.forward_tokens(rows)
-        torch = self._torch
-        lg = torch.from_numpy(logits).to(self.torch_generator.device)
-        probs = torch.zeros((lg.shape[0], 67), device=lg.device)
-        probs[:, :5] = torch.softmax(lg, dim=-1)
+        logits = self._tok_engine.forward_tokens(rows)          # the engine's kernels; ids outside [0, 67) raise (MG_ERR_VOCAB)
+        lg = logits.astype(np.float64)
+        p = np.exp(lg - lg.max(-1, keepdims=True))
+        p /= p.sum(-1, keepdims=True)
         if self._do_sample:
-            acts = []
-            for i in range(0, lg.shape[0], self.cfg.batch_size):
-                acts.append(torch.multinomial(probs[i:i + self.cfg.batch_size], 1, generator=self.torch_generator).squeeze(-1))
-            acts = torch.cat(acts).tolist()
+            # torch.multinomial(probs, 1, generator) == argmax(probs / q), q ~ Exp(1) of shape (rows, 67) drawn per chunk of
+            # batch_size rows (inference.py:88-95); the masked entries have probability 0 and never win
+            torch = self._torch
+            qs = [torch.empty((min(self.cfg.batch_size, len(rows) - i), 67), dtype=torch.float32, device=self.torch_generator.device)
+                  .exponential_(1, generator=self.torch_generator)[:, :5] for i in range(0, len(rows), self.cfg.batch_size)]
+            q = torch.cat(qs).cpu().numpy().astype(np.float64)
+            acts = (p / q).argmax(-1).tolist()
         else:
-            acts = probs.argmax(-1).tolist()
+            acts = p.argmax(-1).tolist()
         out, off = [], 0
         for key, o in zip(positions, observations_list):
             out.append(acts[off:off + len(o)])
