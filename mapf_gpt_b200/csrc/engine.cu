@@ -602,18 +602,25 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         const int ns = std::min(w.chunk_seqs, n_seq - s0);
         const int M = ns * 256, MT = M / 128;
         if (m.fused) {
-            prof_begin(e, KC_EMBED);
             // with >= 2 blocks the first post_attn takes its residual tile from the table itself: the lookup writes q/k/v only
             static const bool x_via_hbm = getenv("MAPF_GPT_B200_BLOCK0_X_VIA_HBM") != nullptr;
             const bool x_from_tab = m.tab0 && m.cfg.n_layer >= 2 && !x_via_hbm;
-            if (m.tab0 && C == 160)
+            // ... and block 0's attention gathers q/k/v from the table itself: no lookup kernel, no q/k/v round trip through HBM
+            // (MAPF_GPT_B200_NO_BLOCK0_GATHER=1 or the classic attention kernel keep the lookup kernel)
+            static const bool no_gather = getenv("MAPF_GPT_B200_NO_BLOCK0_GATHER") != nullptr;
+            const bool gather0 = x_from_tab && hs == 32 && !no_gather && getenv("MAPF_GPT_B200_ATTN_CLASSIC") == nullptr &&
+                                 !(m.cfg.n_layer == 1 && e->prune_last);
+            if (!gather0) prof_begin(e, KC_EMBED);
+            if (gather0) {
+                // nothing to launch
+            } else if (m.tab0 && C == 160)
                 block0_lookup_kernel<160><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, x_from_tab ? nullptr : w.X, w.QKV);
             else if (m.tab0 && C == 256)
                 block0_lookup_kernel<256><<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.tab0, x_from_tab ? nullptr : w.X, w.QKV);
             else
                 embed_ln_kernel<<<MT, 128, 67 * (C + 4) * 4, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe_ti, m.layers[0].ln1,
                                                                           w.X, w.XN, C);
-            prof_end(e);
+            if (!gather0) prof_end(e);
             for (int l = 0; l < m.cfg.n_layer; l++) {
                 const Layer &L = m.layers[l];
                 if ((l == 0 && !m.tab0) || !m.fuse_qkv) {   // blocks >= 1 get q/k/v from the previous block's fused kernel
@@ -645,6 +652,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 at.timeline = e->d_timeline;
                 static const int stamp_item = getenv("MAPF_GPT_B200_STAMP_ITEM") ? atoi(getenv("MAPF_GPT_B200_STAMP_ITEM")) : 40;
                 at.dbg_variant = stamp_item;   // which item of a persistent attention CTA tools/timeline.py stamps
+                if (l == 0 && gather0) { at.tokens0 = tokens + (size_t)s0 * 256; at.tab0 = m.tab0; at.tab_nrec = C / 4 + 3 * C / 8; at.tab_qkv0 = C / 4; }
                 if ((rc = launch_attn(e, at, hs, ns, e->stream, !e->safe_softmax))) return rc;
                 PostAttnArgs pa{};
                 pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.wstream_pair = L.wstream_pair; pa.ln2_gain = L.ln2;

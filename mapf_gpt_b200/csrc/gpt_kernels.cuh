@@ -576,7 +576,18 @@ struct AttnArgs {
     int *work_counter;         // persistent kernel: [0] next unclaimed (sequence, head) item beyond the first gridDim.x,
                                // [1] CTAs finished; both zero between launches (the last CTA resets them)
     long long *timeline;       // test hook: clock64() stamps of CTA 0..3 ([cta][128], ids 100..); nullptr in production
+    // block 0 (attn_persistent_kernel only): q/k/v rows are gathered straight from the L2-resident (token, position) table
+    // instead of being read from `qkv` (block0_lookup_kernel then has nothing to write).  nullptr = read qkv.
+    const uint8_t *tokens0;    // [n_seq * 256] token ids of this chunk
+    const uint4 *tab0;         // [67][256][tab_nrec] records: x (C/4 groups), then q|k|v as [which][head][hs/8] groups of 8 bf16
+    int tab_nrec, tab_qkv0;    // groups per record; first q/k/v group (= C/4)
 };
+__device__ __forceinline__ uint64_t l2_policy_evict_last_attn()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 #define MG_ASTAMP(id)                                                                    \
     do {                                                                                 \
         if (a.timeline != nullptr && blockIdx.x < 4) a.timeline[blockIdx.x * 128 + (id)] = clock64(); \
@@ -1068,19 +1079,19 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * BUF_BYTES);
     uint64_t *full = bars, *empty = bars + 2, *bS = bars + 4, *bP = bars + 5, *bO = bars + 6, *bE = bars + 7;
-    uint64_t *bS1 = bars + 8, *bP1 = bars + 9;   // FAST: second key half (keys 128..255) of S / P
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
     volatile int *item_of = reinterpret_cast<volatile int *>(tmem_slot + 1);   // [2] item held by each buffer, -1 = no more work
     // [2][128] row-max exchange in bf16: both halves of a row read the same two rounded values, and softmax does not care
     // which offset is subtracted -- fp32 here would put the CTA 80 bytes over the two-CTAs-per-SM shared-memory budget
     __nv_bfloat16 *redm = reinterpret_cast<__nv_bfloat16 *>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool gather = a.tab0 != nullptr;
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        // bulk copies: one expect-tx arrival; table gather: every lane of the producer warp arrives after its copies have landed
+        mbar_init(&full[0], gather ? 32 : 1); mbar_init(&full[1], gather ? 32 : 1);
         mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
         mbar_init(bS, 1); mbar_init(bP, 256); mbar_init(bO, 1); mbar_init(bE, 256);
-        mbar_init(bS1, 1); mbar_init(bP1, 256);
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc<256>(tmem_slot);
@@ -1106,7 +1117,42 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
     }
     const size_t blk = (size_t)(HS / 8) * 256 * 8;   // elements per (seq, which, head)
 
-    if (warp == 8) {
+    if (warp == 8 && gather) {
+        // Block 0: the q/k/v rows of a (token, position) pair are a function of that pair alone and sit in the L2-resident table
+        // (Model::tab0).  The whole producer warp gathers them -- 3 x 64 contiguous bytes per token and head -- with 16-byte
+        // cp.async copies straight into the tile images the UMMAs read; a lane owns tokens lane, lane + 32, ...
+        const uint64_t keep = l2_policy_evict_last_attn();
+        int item = blockIdx.x;
+        for (int k = 0;; k++) {
+            const int b = k & 1;
+            mbar_wait(&empty[b], ((k >> 1) & 1) ^ 1);
+            if (item >= n_items) {
+                if (lane == 0) item_of[b] = -1;
+                __syncwarp();
+                mbar_arrive(&full[b]);
+                break;
+            }
+            if (lane == 0) item_of[b] = item;
+            const int head = item % a.n_head, seq = item / a.n_head;
+            uint8_t *buf = smem + b * BUF_BYTES;
+#pragma unroll 2
+            for (int t = lane; t < 256; t += 32) {
+                const int tok = min((int)a.tokens0[(size_t)seq * 256 + t], 66);
+                const uint4 *rec = a.tab0 + ((size_t)tok * 256 + t) * a.tab_nrec + a.tab_qkv0 + head * (HS / 8);
+#pragma unroll
+                for (int which = 0; which < 3; which++)
+#pragma unroll
+                    for (int c = 0; c < HS / 8; c++)
+                        cp_async_16_hint(buf + which * Q_BYTES + (c * 256 + t) * 16, rec + which * a.n_head * (HS / 8) + c, keep);
+            }
+            cp_async_wait_all();
+            fence_proxy_async_smem();              // generic-proxy writes -> visible to the UMMAs' async-proxy reads
+            mbar_arrive(&full[b]);
+            int nxt = 0;
+            if (lane == 0) nxt = (int)gridDim.x + atomicAdd(a.work_counter, 1);
+            item = __shfl_sync(0xffffffffu, nxt, 0);
+        }
+    } else if (warp == 8) {
         if (lane == 0) {
             // items are claimed dynamically: the hardware favours the older of two co-resident CTAs, and with a static split
             // the younger one finished 18 % later, alone on its SM
@@ -1147,51 +1193,6 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
             for (int qt = 0; qt < 2; qt++, t++) {
                 if (t > 0) mbar_wait(bE, (t - 1) & 1);      // previous tile's O drained: the S columns are free
                 tc_fence_after();
-                if constexpr (FAST) {
-                    // Key halves pipelined against the softmax: S_lo and S_hi are separate N = 128 UMMAs with their own commits
-                    // (the workers start on keys 0..127 while S_hi is still being computed), and P_lo V_lo is issued as soon as
-                    // the first half of P is in TMEM, i.e. it runs while the workers exponentiate keys 128..255.
-                    // TMEM: S = [0,256); P_lo = [0,32) | [96,128), P_hi = [128,160) | [224,256) (each thread converts inside its own
-                    // 64 columns); [O | rowsum] = [32,80), inside the first half's columns, which are consumed by then.
-                    constexpr uint32_t idescSh = umma_idesc_bf16(128, 128, 0, 0);
-                    if (elect_one()) {
-                        if (k == 40) MG_ASTAMP(100 + 3 * qt);
-#pragma unroll
-                        for (int ks = 0; ks < HS / 16; ks++)
-                            umma_ss(tmem, umma_desc(qa + qt * 2048 + ks * 2 * 4096, 4096, 128), umma_desc(ka + ks * 2 * 4096, 4096, 128),
-                                    idescSh, ks != 0 ? 1u : 0u);
-                        umma_commit(bS);
-#pragma unroll
-                        for (int ks = 0; ks < HS / 16; ks++)
-                            umma_ss(tmem + 128, umma_desc(qa + qt * 2048 + ks * 2 * 4096, 4096, 128),
-                                    umma_desc(ka + 2048 + ks * 2 * 4096, 4096, 128), idescSh, ks != 0 ? 1u : 0u);
-                        umma_commit(bS1);
-                    }
-                    __syncwarp();
-                    mbar_wait(bP, t & 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        if (k == 40) MG_ASTAMP(101 + 3 * qt);
-#pragma unroll
-                        for (int ks = 0; ks < 8; ks++)
-                            umma_ts(tmem + 32, tmem + (ks < 4 ? ks * 8 : 96 + (ks - 4) * 8), umma_desc(va + ks * 2 * 128, 128, 4096), idescO,
-                                    ks != 0 ? 1u : 0u);
-                    }
-                    __syncwarp();
-                    mbar_wait(bP1, t & 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-#pragma unroll
-                        for (int ks = 8; ks < 16; ks++)
-                            umma_ts(tmem + 32, tmem + (ks < 12 ? 128 + (ks - 8) * 8 : 224 + (ks - 12) * 8), umma_desc(va + ks * 2 * 128, 128, 4096),
-                                    idescO, 1u);
-                        umma_commit(bO);
-                        if (k == 40) MG_ASTAMP(102 + 3 * qt);
-                        if (qt == 1) umma_commit(&empty[b]);   // all UMMAs reading this buffer have retired -> the producer may refill it
-                    }
-                    __syncwarp();
-                    continue;
-                }
                 if (elect_one()) {
                     if (k == 40) MG_ASTAMP(100 + 3 * qt);
 #pragma unroll
@@ -1235,28 +1236,21 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 tc_fence_after();
                 if (stamp) MG_ASTAMP(110 + 8 * qt);
                 if constexpr (FAST) {
-                    // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S.  All 8 warps take key half 0 first
-                    // (the thread pair of a row splits its 128 keys 64 / 64), then half 1: P_lo V_lo runs on the tensor pipe meanwhile.
+                    // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S; 64 columns per TMEM round trip
                     f32x2 unused = pk2(0.f, 0.f);
 #pragma unroll 1
-                    for (int hf = 0; hf < 2; hf++) {
-                        if (hf == 1) {
-                            mbar_wait(bS1, t & 1);
-                            tc_fence_after();
-                        }
+                    for (int cb = 0; cb < 2; cb++) {
                         uint32_t v[64], w[32];
-                        const uint32_t sc0 = trow + hf * 128 + kh * 64;
-                        tmem_ld32(sc0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                        tmem_ld32(sc0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                        tmem_ld32(trow + kh * 128 + cb * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                        tmem_ld32(trow + kh * 128 + cb * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                         tmem_wait_ld();
                         exp2_pack_fast<64, false>(v, w, unused);
-                        const uint32_t pc0 = trow + hf * 128 + kh * 96;     // own columns: [0,32) for kh 0, [96,128) for kh 1
-                        tmem_st16(pc0, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
-                        tmem_st16(pc0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
-                        tmem_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(hf == 0 ? bP : bP1);
+                        tmem_st16(trow + kh * 128 + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
+                        tmem_st16(trow + kh * 128 + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
                     }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bP);
                     if (stamp) MG_ASTAMP(113 + 8 * qt);
                 } else {
                 float mx = -INFINITY;
@@ -1307,9 +1301,8 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 tc_fence_after();
                 if (stamp) MG_ASTAMP(114 + 8 * qt);
                 uint32_t sv[8], v[16];
-                constexpr uint32_t OC = FAST ? 32 : 64;  // first column of [O | rowsum]
-                tmem_ld8(trow + OC + HS, sv);            // row sum
-                tmem_ld16(trow + OC + kh * 16, v);       // 16 of the 32 output columns
+                tmem_ld8(trow + 64 + HS, sv);            // row sum
+                tmem_ld16(trow + 64 + kh * 16, v);       // 16 of the 32 output columns
                 tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive(bE);
@@ -1351,7 +1344,7 @@ done:
     }
     if (warp == 9) tmem_dealloc<256>(tmem);
 }
-constexpr int attn_persistent_smem_bytes() { return 2 * (256 * 32 * 2 * 2 + 256 * 48 * 2) + 10 * 8 + 16 + 512; }
+constexpr int attn_persistent_smem_bytes() { return 2 * (256 * 32 * 2 * 2 + 256 * 48 * 2) + 8 * 8 + 16 + 512; }
 static_assert(2 * (attn_persistent_smem_bytes() + 1024) <= 233472, "two persistent attention CTAs must fit one SM");
 
 // (A one-CTA-per-SM variant with all 16 softmax warps on one query tile and two S tiles in TMEM was measured SLOWER than two

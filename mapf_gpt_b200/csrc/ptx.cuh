@@ -149,6 +149,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         : "memory");
 }
 
+// non-bulk asynchronous 16-byte copy global -> shared (LDGSTS) with an L2 eviction-priority hint; completion by cp_async_wait_all()
+__device__ __forceinline__ void cp_async_16_hint(void *smem_dst, const void *gmem, uint64_t policy)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // L2 prefetch of a contiguous global range (bytes % 16 == 0)
 __device__ __forceinline__ void bulk_prefetch_l2(const void *gmem, uint32_t bytes)
 {

@@ -1,0 +1,21 @@
+#!/bin/bash
+# A/B: block 0's attention gathers q/k/v from the (token, position) table (no lookup kernel) vs the lookup kernel
+cd "$(dirname "$0")/.."
+O=gpurun_out/r02m; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py tests/test_gpu_rollout.py -m gpu -x -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -4 $O/tests.log
+run() { name=$1; shift
+  env "$@" timeout 300 python bench.py --quick --steps 8 --warmup 3 > $O/b2M_$name.json 2>$O/b2M_$name.err
+  env "$@" timeout 300 python bench.py --quick --steps 4 --warmup 3 --model 6M --map wfi_warehouse --agents 192 --envs 512 > $O/b6M_$name.json 2>$O/b6M_$name.err
+  python - <<PY
+import json
+for f in ("$O/b2M_$name.json","$O/b6M_$name.json"):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, round(d['value']), d['roofline']['whole_step_frac'], {k:v['avg_ms'] for k,v in d['kernels'].items() if v['share']>0.015}, d['clocks']['sm_mhz'])
+    except Exception as ex: print(f,'ERR',ex, open(f.replace('.json','.err')).read()[-800:])
+PY
+}
+run gather X=1
+run lookup MAPF_GPT_B200_NO_BLOCK0_GATHER=1
+run gather2 X=1
+run lookup2 MAPF_GPT_B200_NO_BLOCK0_GATHER=1
