@@ -151,10 +151,7 @@ struct PostAttnCfg {
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
     static constexpr int THREADS = 64 + 256 * NT;
     static constexpr int QKV_STAGES = 6 * NFC / U;     // next block's c_attn: 6 half n-tiles of HC columns (FC-chunk stage format)
-    // two FC accumulators when TMEM has room (C = 256: 256 + 2 * 128 = 512 columns): FC(j+1) is issued without waiting for
-    // the workers to drain FC(j), so the "wait for the FC chunk" of the MLP loop disappears (C = 160: 160 + 2 * 80 > 256)
-    static constexpr bool FC2 = NT == 1 && (C + 2 * HC) <= TILE_COLS;
-    static constexpr int NBAR = 3 * STAGES + 2 + NT * 16;
+    static constexpr int NBAR = 3 * STAGES + 2 + NT * 14;
     static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * SLOT_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
     static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
@@ -204,9 +201,9 @@ post_attn_kernel(const PostAttnArgs a)
     uint64_t *bar_att = bar_done + 1;    // [NT] A tile landed (tx)
     uint64_t *bar_x = bar_att + NT;      // [NT] x pre-loaded into the TMEM accumulator (256 arrivals)
     uint64_t *bar_ln2 = bar_x + NT;      // [NT] LN2(x1) in smem (256 arrivals)
-    uint64_t *bar_a1f = bar_ln2 + NT;    // [NT][2] FC chunk accumulated (second entry: the odd chunks' accumulator when K::FC2)
-    uint64_t *bar_a1e = bar_a1f + 2 * NT;  // [NT][2] FC chunk drained to registers (256 arrivals)
-    uint64_t *bar_hf = bar_a1e + 2 * NT; // [NT] hidden chunk written to smem (256 arrivals)
+    uint64_t *bar_a1f = bar_ln2 + NT;    // [NT] FC chunk accumulated
+    uint64_t *bar_a1e = bar_a1f + NT;    // [NT] FC chunk drained to registers (256 arrivals)
+    uint64_t *bar_hf = bar_a1e + NT;     // [NT] hidden chunk written to smem (256 arrivals)
     uint64_t *bar_he = bar_hf + NT;      // [NT] hidden chunk consumed by the proj2 UMMAs
     uint64_t *bar_qa = bar_he + NT;      // [NT] fused QKV: LN1_next(x') in smem, accumulator free (256 arrivals)
     uint64_t *bar_qf = bar_qa + NT;      // [NT][3] fused QKV: half n-tile accumulated in buffer b
@@ -281,10 +278,8 @@ post_attn_kernel(const PostAttnArgs a)
         for (int t = 0; t < NT; t++) {
             mbar_init(&bar_x[t], WARR + (PAIR ? 1 : 0));   // + the peer's "att tile landed" relay
             mbar_init(&bar_ln2[t], WARR);
-            for (int b = 0; b < 2; b++) {
-                mbar_init(&bar_a1f[2 * t + b], 1);
-                mbar_init(&bar_a1e[2 * t + b], WARR);
-            }
+            mbar_init(&bar_a1f[t], 1);
+            mbar_init(&bar_a1e[t], WARR);
             mbar_init(&bar_hf[t], WARR);
             mbar_init(&bar_he[t], 1);
             mbar_init(&bar_qa[t], WARR);
@@ -431,15 +426,9 @@ post_attn_kernel(const PostAttnArgs a)
                     const uint32_t b = stage_wait(i);
 #pragma unroll
                     for (int t = 0; t < NT; t++) {
-                        // K::FC2: chunk j accumulates in buffer j & 1; it only has to wait for the drain of chunk j - 2
-                        const int fb = K::FC2 ? (j & 1) : 0;
                         if (st == 0) {
                             if (j == 0) mbar_wait(&bar_ln2[t], ph);
-                            if (K::FC2) {
-                                if (j >= 2) mbar_wait(&bar_a1e[2 * t + fb], ((j >> 1) - 1) & 1);
-                            } else if (j >= 1) {
-                                mbar_wait(&bar_a1e[2 * t], (j - 1) & 1);
-                            }
+                            else mbar_wait(&bar_a1e[t], (j - 1) & 1);
                             tc_fence_after();
                         }
                         if (elect_one()) {
@@ -447,11 +436,11 @@ post_attn_kernel(const PostAttnArgs a)
                             for (int u = 0; u < U; u++)
 #pragma unroll
                                 for (int ks = 0; ks < 2; ks++)
-                                    mma(tmem + t * K::TILE_COLS + C + fb * HC,
+                                    mma(tmem + t * K::TILE_COLS + C,
                                         umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
                                         umma_desc(b + u * UNIT_B + ks * 2 * (HB * 16), HB * 16, 128), idescH,
                                         (st | u | ks) != 0);
-                            if (st == K::NFC / U - 1) commit(&bar_a1f[2 * t + fb]);
+                            if (st == K::NFC / U - 1) commit(&bar_a1f[t]);
                             if (t == NT - 1) {
                                 commit(&empty[i % S]);
                                 if (st == K::NFC / U - 1) MG_STAMP(10 + 2 * j);
@@ -632,17 +621,16 @@ post_attn_kernel(const PostAttnArgs a)
         // cap and delays the hidden-chunk hand-off whenever FC(j+1) is late.  Same for the q/k/v drain below.)
 #pragma unroll 1
         for (int j = 0; j < K::NCH; j++) {
-            const int fb = K::FC2 ? (j & 1) : 0;
-            mbar_wait(&bar_a1f[2 * t + fb], (K::FC2 ? (j >> 1) : j) & 1);
+            mbar_wait(&bar_a1f[t], j & 1);
             tc_fence_after();
             MG_WLAP(3);  // waiting for the FC chunk
             if (threadIdx.x == 0) MG_STAMP(60 + 3 * j);
             uint32_t v[NV][8];
 #pragma unroll
-            for (int g = 0; g < NV; g++) tmem_ld8(trow + C + fb * HC + h * HH + g * 8, v[g]);
+            for (int g = 0; g < NV; g++) tmem_ld8(trow + C + h * HH + g * 8, v[g]);
             tmem_wait_ld();
             tc_fence_before();
-            arrive_issuer(&bar_a1e[2 * t + fb]);
+            arrive_issuer(&bar_a1e[t]);
             MG_WLAP(4);  // FC chunk -> registers
             if (threadIdx.x == 0) MG_STAMP(61 + 3 * j);
             uint4 o[NV];
