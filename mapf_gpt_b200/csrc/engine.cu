@@ -607,7 +607,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             const bool x_from_tab = m.tab0 && m.cfg.n_layer >= 2 && !x_via_hbm;
             // ... and block 0's attention gathers q/k/v from the table itself: no lookup kernel, no q/k/v round trip through HBM
             // (MAPF_GPT_B200_NO_BLOCK0_GATHER=1 or the classic attention kernel keep the lookup kernel)
-            static const bool no_gather = getenv("MAPF_GPT_B200_NO_BLOCK0_GATHER") != nullptr;
+            const bool no_gather = getenv("MAPF_GPT_B200_NO_BLOCK0_GATHER") != nullptr;   // per forward: tests flip it between engines
             const bool gather0 = x_from_tab && hs == 32 && !no_gather && getenv("MAPF_GPT_B200_ATTN_CLASSIC") == nullptr &&
                                  !(m.cfg.n_layer == 1 && e->prune_last);
             if (!gather0) prof_begin(e, KC_EMBED);

@@ -229,13 +229,18 @@ def test_block0_lookup_table_is_bit_identical_to_the_computed_block0(dev, name, 
     toks = np.concatenate([np.repeat(np.arange(67, dtype=np.int8)[:, None], 256, 1),      # every (token, position) pair
                            rng.integers(0, 67, (61, 256)).astype(np.int8)])
     outs = []
-    for off in (None, "1"):
-        if off: monkeypatch.setenv("MAPF_GPT_B200_NO_BLOCK0_TABLE", off)
+    # default: x is gathered from the table by the first post_attn, q/k/v by the first attention launch (no block-0 kernel);
+    # then the lookup kernel writing q/k/v to HBM; then no table at all (embedding + ln_1 + c_attn computed per step)
+    for env in ({}, {"MAPF_GPT_B200_NO_BLOCK0_GATHER": "1"}, {"MAPF_GPT_B200_NO_BLOCK0_TABLE": "1"}):
+        for k in ("MAPF_GPT_B200_NO_BLOCK0_GATHER", "MAPF_GPT_B200_NO_BLOCK0_TABLE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         eng = E.RolloutEngine(1, 1, 11, 11)
         eng.load_model(sd, cfg)
         outs.append(eng.forward_tokens(toks))
         eng.close()
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
 def test_generic_path_kernel_variants_agree(dev, monkeypatch):
