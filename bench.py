@@ -233,7 +233,8 @@ def kernel_table(model_cfg, ktimes, total_ms, seqs_per_gpu, pk):
     pruned = fused_path and os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1"
     fuse_qkv = fused_path and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
     table0 = fuse_qkv and os.environ.get("MAPF_GPT_B200_NO_BLOCK0_TABLE") is None
-    rows_per_launch = min(seqs_per_gpu, 8192) * T            # the engine forwards in chunks of 8192 sequences
+    chunk = int(os.environ.get("MAPF_GPT_B200_CHUNK_SEQS", "8192")) // 128 * 128
+    rows_per_launch = min(seqs_per_gpu, max(chunk, 128)) * T  # the engine forwards in chunks of 8192 sequences (env override)
     kflops = {"gemm_qkv": 2 * 3 * C * C, "gemm_attn_proj": 2 * C * C, "gemm_fc_gelu": 2 * 4 * C * C,
               "gemm_mlp_proj": 2 * 4 * C * C, "attention": 4 * T * C, "post_attn_fused": 2 * 9 * C * C}   # per token
     if fuse_qkv:

@@ -509,7 +509,9 @@ static int ensure_workspace(mg_engine *e, int want_seqs)
 {
     Workspace &w = e->ws;
     const int C = e->model.cfg.n_embd;
-    int chunk = std::min(want_seqs, 8192);
+    // sequences per forward chunk (workspace = 22 * chunk * 256 * C bytes); MAPF_GPT_B200_CHUNK_SEQS overrides (multiple of 128)
+    static const int chunk_max = getenv("MAPF_GPT_B200_CHUNK_SEQS") ? std::max(128, atoi(getenv("MAPF_GPT_B200_CHUNK_SEQS")) / 128 * 128) : 8192;
+    int chunk = std::min(want_seqs, chunk_max);
     if (chunk <= w.chunk_seqs) return MG_OK;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
     w.X = w.Xc = w.STATS = nullptr; w.XN = w.QKV = w.ATT = w.HID = w.ATTc = nullptr; w.chunk_seqs = 0;
