@@ -132,6 +132,11 @@ int mg_engine_set_max_episode_steps(mg_engine *e, int n);
 
 /* forward only, for tests: tokens HOST int8 [n_rows][256] -> logits HOST fp32 [n_rows][5] */
 int mg_engine_forward_tokens(mg_engine *e, const int8_t *tokens, int n_rows, float *logits_out);
+/* Validation loss of the training objective on dataset rows (train.py:244-258 estimate_loss; model.py:180-183 with targets:
+ * cross-entropy over the 67 tied lm_head logits of position 255, ignore_index -1; dataset/fast_data_loader.py:57 puts the
+ * ground-truth action there).  tokens: int8 [n_rows][256] as the Arrow shards hold them (generate_dataset.py:188-191),
+ * targets: int8 [n_rows] (-1 = ignore -> loss 0); loss_out: float [n_rows]; pred_out: int32 [n_rows] arg-max action (0..4). */
+int mg_engine_eval_tokens(mg_engine *e, const int8_t *tokens, const int8_t *targets, int n_rows, float *loss_out, int32_t *pred_out);
 
 /* ---- POGEMA `soft` step on the device -------------------------- */
 /* Applies `actions` (HOST, may be NULL = the actions mg_engine_act sampled) with collision

@@ -62,6 +62,7 @@ _SIGS = {
     "mg_engine_set_env_offset": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_engine_set_max_episode_steps": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_engine_forward_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "mg_engine_eval_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mg_engine_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_engine_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mg_engine_act_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

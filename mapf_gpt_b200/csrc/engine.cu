@@ -591,11 +591,29 @@ static int forward_precise(mg_engine *e, const uint8_t *tokens, int n_seq, float
 }
 
 // tokens (device, uint8 [n_seq][256]) -> logits (device, fp32 [n_seq][8])
-static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float *logits)
+// optional per-sequence validation outputs of forward_device (mg_engine_eval_tokens): device pointers, all three or none
+struct EvalOut {
+    const int8_t *targets = nullptr;   // [n_seq] ground-truth action of each row, -1 = ignore
+    float *loss = nullptr;             // [n_seq] cross-entropy over the 67 logits of position 255
+    int32_t *pred = nullptr;           // [n_seq] arg-max action
+};
+static void launch_head_loss(mg_engine *e, const float *X, int compact, const EvalOut &ev, int s0, int ns)
+{
+    const Model &m = e->model;
+    const int C = m.cfg.n_embd;
+    e->launches++;
+    head_loss_kernel<<<(ns + 3) / 4, 128, 4 * C * sizeof(float), e->stream>>>(X, compact, m.lnf, m.wte, ev.targets + s0, ev.loss + s0,
+                                                                             ev.pred + s0, C, ns);
+}
+
+static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float *logits, const EvalOut *ev = nullptr)
 {
     Model &m = e->model;
     if (!m.loaded) return fail(MG_ERR_STATE, "forward: no model loaded (mg_engine_load_model)");
-    if (e->precise) return forward_precise(e, tokens, n_seq, logits);
+    if (e->precise) {
+        if (ev) return fail(MG_ERR_STATE, "validation loss is not available in the fp32 verification mode");
+        return forward_precise(e, tokens, n_seq, logits);
+    }
     int rc = ensure_workspace(e, n_seq);
     if (rc) return rc;
     Workspace &w = e->ws;
@@ -646,6 +664,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                     prof_begin(e, KC_HEAD);
                     head_compact_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.Xc, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
                     prof_end(e);
+                    if (ev) launch_head_loss(e, w.Xc, 1, *ev, s0, ns);
                     break;
                 }
                 AttnArgs at{};
@@ -670,6 +689,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             prof_begin(e, KC_HEAD);
             head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.X, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
             prof_end(e);
+            if (ev) launch_head_loss(e, w.X, 0, *ev, s0, ns);
             continue;
         }
         const bool lnf = m.ln_fused;    // ln_1 / ln_2 live in the epilogues of the GEMMs around them; w.XN holds the RAW bf16 residual
@@ -712,6 +732,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         prof_begin(e, KC_HEAD);
         head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.X, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
         prof_end(e);
+        if (ev) launch_head_loss(e, w.X, 0, *ev, s0, ns);
     }
     CU(cudaGetLastError());
     return MG_OK;
@@ -1449,6 +1470,42 @@ int mg_engine_forward_tokens(mg_engine *e, const int8_t *tokens, int n_rows, flo
     CU(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < n_rows; i++) memcpy(logits_out + (size_t)i * 5, tmp.data() + (size_t)i * 8, 20);
     if (e->profiling) prof_collect(e);
+    return MG_OK;
+}
+
+int mg_engine_eval_tokens(mg_engine *e, const int8_t *tokens, const int8_t *targets, int n_rows, float *loss_out, int32_t *pred_out)
+{
+    if (!e || !tokens || !targets || !loss_out || !pred_out || n_rows < 1) return fail(MG_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < (size_t)n_rows * 256; i++)
+        if (tokens[i] < 0 || tokens[i] >= MG_VOCAB)
+            return fail(MG_ERR_VOCAB, "row %zu token %zu: id %d outside the vocabulary [0, %d)", i / 256, i % 256, (int)tokens[i], MG_VOCAB);
+    for (int i = 0; i < n_rows; i++)
+        if (targets[i] < -1 || targets[i] >= MG_VOCAB) return fail(MG_ERR_VOCAB, "row %d: target %d outside [-1, %d)", i, (int)targets[i], MG_VOCAB);
+    CU(cudaSetDevice(e->device));
+    Workspace &w = e->ws;
+    cudaFree(w.tok); cudaFree(w.logits);
+    w.tok = nullptr; w.logits = nullptr;
+    CU(dalloc(&w.tok, (size_t)n_rows * 256));
+    CU(dalloc(&w.logits, (size_t)n_rows * 8));
+    int8_t *d_tgt = nullptr;
+    float *d_loss = nullptr;
+    int32_t *d_pred = nullptr;
+    CU(dalloc(&d_tgt, (size_t)n_rows));
+    CU(dalloc(&d_loss, (size_t)n_rows));
+    CU(dalloc(&d_pred, (size_t)n_rows));
+    CU(cudaMemcpyAsync(w.tok, tokens, (size_t)n_rows * 256, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_tgt, targets, (size_t)n_rows, cudaMemcpyHostToDevice, e->stream));
+    EvalOut ev;
+    ev.targets = d_tgt; ev.loss = d_loss; ev.pred = d_pred;
+    int rc = forward_device(e, w.tok, n_rows, w.logits, &ev);
+    if (!rc) {
+        cudaMemcpyAsync(loss_out, d_loss, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, e->stream);
+        cudaMemcpyAsync(pred_out, d_pred, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, e->stream);
+    }
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_tgt); cudaFree(d_loss); cudaFree(d_pred);
+    if (rc) return rc;
+    if (err != cudaSuccess) return fail(MG_ERR_CUDA, "eval_tokens: %s", cudaGetErrorString(err));
     return MG_OK;
 }
 

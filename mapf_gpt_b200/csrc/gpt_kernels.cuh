@@ -1489,6 +1489,86 @@ __global__ void __launch_bounds__(256, 2) ln_rows_kernel(const float *__restrict
     }
 }
 
+// Validation loss of the training objective (train.py:244-258, model.py:180-183): ln_f on the LAST token of each sequence, ALL 67
+// tied lm_head logits, cross-entropy against the ground-truth action of a dataset row (F.cross_entropy with ignore_index = -1:
+// only position 255 carries a target, dataset/fast_data_loader.py:57) and the arg-max action.  One warp per sequence; a lane
+// owns logits lane, lane + 32, lane + 64.  compact = 1: X holds one row per sequence (last-block pruning), else tile images.
+__global__ void __launch_bounds__(128) head_loss_kernel(const float *__restrict__ X, int compact, const float *__restrict__ gain,
+                                                        const float *__restrict__ wte, const int8_t *__restrict__ targets,
+                                                        float *__restrict__ loss, int32_t *__restrict__ pred, int C, int n_seq)
+{
+    extern __shared__ float hl_y[];                    // [4 warps][C] normalised row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seq = blockIdx.x * 4 + warp;
+    if (seq >= n_seq) return;
+    const float4 *Xi = compact ? reinterpret_cast<const float4 *>(X) + (size_t)(seq >> 7) * (C / 4) * 128 + (seq & 127)
+                               : reinterpret_cast<const float4 *>(X) + (size_t)(seq * 2 + 1) * (C / 4) * 128 + 127;
+    float s = 0.f;
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 v = Xi[(size_t)c4 * 128];
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 v = Xi[(size_t)c4 * 128];
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + 1e-5f);
+    float *y = hl_y + warp * C;
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+        const float4 v = Xi[(size_t)c4 * 128];
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gain) + c4);
+        reinterpret_cast<float4 *>(y)[c4] = make_float4((v.x - mean) * rstd * g.x, (v.y - mean) * rstd * g.y,
+                                                       (v.z - mean) * rstd * g.z, (v.w - mean) * rstd * g.w);
+    }
+    __syncwarp();
+    float lg[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int k = lane + 32 * i;
+        if (k < 67) {
+            const float4 *w = reinterpret_cast<const float4 *>(wte + (size_t)k * C);
+            float acc = 0.f;
+            for (int c4 = 0; c4 < C / 4; c4++) {
+                const float4 a = reinterpret_cast<const float4 *>(y)[c4], b = __ldg(w + c4);
+                acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            }
+            lg[i] = acc;
+        }
+    }
+    float mx = fmaxf(fmaxf(lg[0], lg[1]), lg[2]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        if (lane + 32 * i < 67) se += expf(lg[i] - mx);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse = mx + logf(se);
+    const int tgt = targets[seq];
+    const float lt = __shfl_sync(0xffffffffu, tgt >= 32 ? (tgt >= 64 ? lg[2] : lg[1]) : lg[0], tgt < 0 ? 0 : (tgt & 31));
+    // arg-max over the 5 action logits (GPT.act masks the rest, model.py:249-252): lanes 0..4 hold them in lg[0]
+    float bv = lane < 5 ? lg[0] : -INFINITY;
+    int bi = lane;
+#pragma unroll
+    for (int o = 4; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        loss[seq] = (tgt < 0 || tgt >= 67) ? 0.f : lse - lt;
+        pred[seq] = bi;
+    }
+}
+
 // ln_f on the LAST token of each sequence + the 5 action logits (tied lm_head rows 0..4),
 // model.py:178,186,249-252.  One warp per sequence.
 __global__ void __launch_bounds__(128) head_kernel(const float *__restrict__ X, const float *__restrict__ gain,

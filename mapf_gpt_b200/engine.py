@@ -137,6 +137,17 @@ class RolloutEngine:
         _lib.check(self._L.mg_engine_forward_tokens(self._h, _ptr(t), t.shape[0], _ptr(out)))
         return out
 
+    def eval_tokens(self, tokens, targets):
+        """Dataset rows -> (cross-entropy of the training objective per row, arg-max action per row): model.py:180-183 with
+        targets only at position 255 (dataset/fast_data_loader.py:57).  tokens int8 [n, 256], targets int8 [n] (-1 = ignore)."""
+        t = np.ascontiguousarray(tokens, dtype=np.int8)
+        y = np.ascontiguousarray(targets, dtype=np.int8)
+        assert t.ndim == 2 and t.shape[1] == 256 and y.shape == (t.shape[0],)
+        loss = np.empty(t.shape[0], dtype=np.float32)
+        pred = np.empty(t.shape[0], dtype=np.int32)
+        _lib.check(self._L.mg_engine_eval_tokens(self._h, _ptr(t), _ptr(y), t.shape[0], _ptr(loss), _ptr(pred)))
+        return loss, pred
+
     def env_step(self, actions=None, fetch: bool = True):
         a = self._pad(actions, 0)
         out = np.empty((self.num_envs, self.N, 2), dtype=np.int32) if fetch else None

@@ -347,3 +347,42 @@ def test_fresh_process_forward_stress():
         r = subprocess.run([sys.executable, str(ROOT / "tools" / "stress_forward.py"), name, str(n_seq), str(iters)],
                            capture_output=True, text=True, timeout=120, cwd=ROOT)
         assert r.returncode == 0 and "done" in r.stdout, (i, name, r.stdout[-500:], r.stderr[-1500:])
+
+
+# ------------------------------------------------------------------------------------------------ training-side reuse (8f.4)
+@pytest.mark.parametrize("name", ["2M", "85M"])
+def test_validation_loss_on_arrow_shards_matches_the_reference_objective(built, tmp_path, name):
+    """estimate_loss (train.py:244-258) on shards in the reference's Arrow format: the engine's per-row cross-entropy over the 67
+    tied lm_head logits of position 255 (model.py:180-183, ignore_index -1) and its arg-max action against the fp32 oracle."""
+    from mapf_gpt_b200 import dataset as D, engine as E
+    from oracle import gpt_oracle as G
+    cfg, sd = sharp_model(name)
+    rng = np.random.default_rng(7)
+    n = 300
+    x = rng.integers(0, 67, (n, 256)).astype(np.int8)
+    y = rng.integers(0, 5, n).astype(np.int8)
+    y[::17] = -1                                               # ignored rows contribute nothing
+    (tmp_path / "validation").mkdir()
+    D.write_shard(tmp_path / "validation" / "v_part_0.arrow", x[:150], y[:150])
+    D.write_shard(tmp_path / "validation" / "v_part_1.arrow", x[150:], y[150:])
+    eng = E.RolloutEngine(1, 1, 11, 11)
+    eng.load_model(sd, cfg)
+    loss, pred = eng.eval_tokens(x, y)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdd = {k: v.cuda() for k, v in sd.items()}
+    logits = torch.cat([G.forward_logits(sdd, cfg.n_layer, cfg.n_head, torch.from_numpy(x[i:i + 50].astype(np.int64)).cuda())
+                        for i in range(0, n, 50)])
+    ref = torch.nn.functional.cross_entropy(logits, torch.from_numpy(y.astype(np.int64)).cuda(), ignore_index=-1, reduction="none").cpu().numpy()
+    assert np.abs(loss - ref).max() < 2 * LOGIT_TOL, np.abs(loss - ref).max()
+    assert (loss[y < 0] == 0).all()
+    srt = np.sort(logits[:, :5].cpu().numpy(), -1)
+    dec = (srt[:, -1] - srt[:, -2]) > 2 * LOGIT_TOL
+    assert (pred[dec] == logits[:, :5].argmax(-1).cpu().numpy()[dec]).all()
+    ds = D.MapfArrowDataset(tmp_path / "validation", device="cuda", batch_size=150, seed=3)
+    out = D.estimate_loss(eng, iter(ds), eval_iters=2)          # 2 batches of 150 = both shards once
+    valid = y >= 0
+    assert out["rows"] == int(valid.sum())
+    assert abs(out["accuracy"] - float((pred[valid] == y[valid]).mean())) < 1e-9
+    want = np.mean([loss[:150][valid[:150]].mean(), loss[150:][valid[150:]].mean()])     # mean of the batch means (train.py:248-256)
+    assert abs(out["loss"] - want) < 1e-5
+    eng.close()

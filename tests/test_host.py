@@ -1,5 +1,6 @@
 """CPU: host-side logic and the C-ABI library's load/export contract (no compute without a GPU)."""
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -151,3 +152,36 @@ def test_benchmark_yaml_axes_and_tabular_view():
     header, rows = bm.tabular_view(recs, {"type": "tabular", "drop_keys": ["seed", "map_name", "runtime"]}, ["num_agents", "map_name"])
     assert header == ["algorithm", "num_agents", "CSR", "ISR", "SoC", "makespan", "ep_length", "avg_agents_density", "episodes"]
     assert rows == [["A", 8] + [9.0] * 6 + [3], ["A", 16] + [17.0] * 6 + [3]]
+
+
+def test_arrow_shard_reader_mirrors_the_reference_loader(tmp_path, monkeypatch):
+    """mapf_gpt_b200.dataset (first slice): shards in the reference's schema (generate_dataset.py:188-191) read back the
+    way dataset/fast_data_loader.py reads them; batches carry -1 targets except at the last position; `train` folders are split
+    over LOCAL_RANK / WORLD_SIZE."""
+    import pyarrow as pa
+    from mapf_gpt_b200 import dataset as D
+    rng = np.random.default_rng(0)
+    (tmp_path / "train").mkdir()
+    shards = []
+    for i in range(4):
+        x = rng.integers(0, 67, (50, 256)).astype(np.int8)
+        y = rng.integers(0, 5, 50).astype(np.int8)
+        D.write_shard(tmp_path / "train" / f"chunk_part_{i}.arrow", x, y)
+        shards.append((x, y))
+    with pa.memory_map(str(tmp_path / "train" / "chunk_part_2.arrow")) as src:      # the reference's own reading code (:38-43)
+        table = pa.ipc.open_file(src).read_all()
+        assert table.schema.names == ["input_tensors", "gt_actions"]
+        assert (np.stack(table["input_tensors"].to_numpy(zero_copy_only=False)) == shards[2][0]).all()
+        assert (table["gt_actions"].to_numpy(zero_copy_only=False) == shards[2][1]).all()
+    ds = D.MapfArrowDataset(tmp_path / "train", device="cuda", batch_size=32, seed=0)
+    assert ds.get_full_dataset_size() == 200 and ds.get_shard_size() == 200
+    it = iter(ds)
+    xb, tb = next(it)
+    assert xb.shape == (32, 256) and tb.shape == (32, 256) and xb.dtype == np.int8 and (tb[:, :-1] == -1).all()
+    rows = {bytes(r) for r in shards[0][0]}
+    assert all(bytes(r) in rows for r in xb)                                       # first file, shuffled inside the file
+    monkeypatch.setenv("LOCAL_RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    part = D.MapfArrowDataset(tmp_path / "train", batch_size=64)
+    assert [os.path.basename(p) for p in part.file_paths] == ["chunk_part_2.arrow", "chunk_part_3.arrow"]
+    assert part.get_shard_size() == 100 and part.get_full_dataset_size() == 200
