@@ -72,23 +72,60 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md): NVML when nvidia_ml_py is importable (a sample
+    costs microseconds, so short timed regions still get many), else the nvidia-smi query of the recipe."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu, self.rows, self._stop_ev = gpu_index, [], threading.Event()
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:                                    # NVML counts physical devices
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if gpu_index < len(ids) and ids[gpu_index].strip().isdigit():
+                    idx = int(ids[gpu_index])
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            self._h = None
 
     def run(self):
         while not self._stop_ev.is_set():
+            if self._h is not None:
+                try:
+                    nv = self._nv
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit, name in self.NVML_REASONS.items():
+                        if bits & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    self._h = None
+                    continue
+                self._stop_ev.wait(0.02)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                    r = [c.strip() for c in line.split(",")]
+                    if len(r) >= 8 and r[1].replace(".", "").isdigit():
+                        self.sm.append(float(r[1]))
+                        self.mx.append(float(r[2]))
+                        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                        self.reasons.update(names[i] for i in range(4) if r[4 + i].lower().startswith("active"))
             except Exception:
                 pass
             self._stop_ev.wait(0.15)
@@ -96,12 +133,10 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_ev.set()
         self.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": round(max(self.power), 1) if self.power else None,
+                "source": "nvml" if self.power else "nvidia-smi"}
 
 
 def build_instances(map_name, n_agents, n_envs, first_env, seed=0):
