@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 first GPU pass: tests, then A/B of the max-free softmax on the three model sizes
 mkdir -p gpurun_out/r02a
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/r02a/gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02a/tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r02a/tests.log
 tail -15 gpurun_out/r02a/tests.log

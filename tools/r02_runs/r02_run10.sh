@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 evidence pass: whole GPU suite, the default bench (every config + comparators), the reference arm, ncu captures
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02j; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -4 $O/tests.log
 ( time timeout 900 python bench.py ) > $O/bench_default.json 2> $O/bench_default.err; echo "bench rc=$?"; tail -4 $O/bench_default.err

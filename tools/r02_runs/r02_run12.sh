@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2-GPU pass: bench.py under torchrun exactly as the driver launches it (+ the reference arm), the two-devices-in-one-process test,
 # benchmark.py sharded over 2 ranks
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02l; mkdir -p $O
 nvidia-smi -L > $O/gpus.txt
 timeout 600 python -m pytest tests/test_gpu_round2.py -m gpu -q -k "two_devices or pre_tokenized or dropin" > $O/tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/tests.log

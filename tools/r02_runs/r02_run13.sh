@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B: block 0's attention gathers q/k/v from the (token, position) table (no lookup kernel) vs the lookup kernel
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02m; mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py tests/test_gpu_rollout.py -m gpu -x -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -4 $O/tests.log
 run() { name=$1; shift

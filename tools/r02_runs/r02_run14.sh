@@ -1,6 +1,6 @@
 #!/bin/bash
 # final evidence pass of round 2: whole GPU suite, smoke, default bench (+ reference arm), ncu launch lists / full captures
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02n; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -4 $O/tests.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer memcheck over the round-2 kernels (table-gathering attention, LayerNorm-folded GEMM epilogues, fp32 verification
 # forward, density metric, persistent post_attn<256>): smoke() + a test subset
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02p; mkdir -p $O
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/san_smoke.txt 2>&1; echo "smoke memcheck rc=$?"; tail -3 $O/san_smoke.txt
 timeout 2400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py -m gpu -x -q \

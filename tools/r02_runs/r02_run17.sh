@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B: sequences per forward chunk
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02q; mkdir -p $O
 run() { name=$1; shift
   env "$@" timeout 300 python bench.py --quick --steps 8 --warmup 3 > $O/b2M_$name.json 2>$O/b2M_$name.err

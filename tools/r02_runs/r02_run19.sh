@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU pass, launched as the driver does: the default bench (C2 headline + every other config; its C4 entry IS BASELINE's C4:
 # Berlin tile, 256 agents x 32 envs per GPU x 8 GPUs, MAPF-GPT-85M) and the reference arm
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02s; mkdir -p $O
 nvidia-smi -L > $O/gpus.txt
 ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 8 --warmup 3 ) > $O/bench_n8.json 2> $O/bench_n8.err; echo "bench n8 rc=$?"; tail -4 $O/bench_n8.err

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 second GPU pass: all GPU tests, the full default bench (every config + comparators), the reference arm,
 # the YAML benchmark smoke, and the attention polynomial-share A/B
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02b; mkdir -p $O
 timeout 1200 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?" | tee -a $O/tests.log
 tail -5 $O/tests.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02t; mkdir -p $O
 timeout 300 python bench.py --quick --steps 8 --warmup 3 > $O/b2M.json 2>$O/b2M.err
 python - <<'PY'

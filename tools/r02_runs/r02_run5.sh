@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the persistent post_attn launch: stagger spread and grid size
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02e; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_rollout.py -m gpu -x -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/tests.log
 run() { # name, env...

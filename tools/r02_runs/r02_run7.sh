@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B: MUFU.TANH GELU vs the FMA-only polynomial; default persistent policy (C=256 only)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02g; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_rollout.py -m gpu -x -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/tests.log
 MAPF_GPT_B200_LIB_PATH=$PWD/mapf_gpt_b200/libvar_gelu_tanh.so timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py -m gpu -q -k "forward or logit or fused" > $O/tests_tanh.log 2>&1; echo "tanh tests rc=$?"; tail -3 $O/tests_tanh.log

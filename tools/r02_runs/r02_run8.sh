@@ -1,6 +1,6 @@
 #!/bin/bash
 # GELU forms A/B (logistic default, tanh, FMA-only polynomial) + whole GPU suite + flip rates + the full YAML benchmark
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02h; mkdir -p $O
 timeout 1200 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/tests.log
 python tools/flip_rate.py > $O/flip_rate.txt 2>&1; cat $O/flip_rate.txt | cut -c1-250

@@ -1,6 +1,6 @@
 #!/bin/bash
 # LayerNorm folded into the 85M pair GEMMs: tests + A/B (MAPF_GPT_B200_LN_FUSED=0 keeps the LayerNorm kernel)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out/r02i; mkdir -p $O
 timeout 1200 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py tests/test_gpu_rollout.py -m gpu -x -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -5 $O/tests.log
 python tools/flip_rate.py 85M > $O/flip_85M.txt 2>&1; cut -c1-330 $O/flip_85M.txt
