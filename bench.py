@@ -20,7 +20,8 @@ POGEMA soft step.
                  MAPFGPTInference.act() (32 agents x 1 env, obs dicts in, list out, median of 60 calls)
   cpu_baseline   the UNMODIFIED reference (mapf_gpt/inference.py + model.py + compiled generator from baseline/_ref,
                  oracle/ref_runtime.py) on the host cores: act_batch with all torch threads ("fair");
-  cpu_as_shipped the same through one act() per env with OpenMP pinned to one thread by the generator (as shipped)
+  cpu_as_shipped the same through one act() per env with OpenMP pinned to one thread by the generator (as shipped);
+  cpu_fair_processes: one such single-thread worker process per host core, the reference's own scaling model (num_process)
   stock_gpu      the same reference object with device='cuda' (inference.py:58-60): stock PyTorch fp32 kernels and a
                  bf16-autocast variant, tokenizer on the host as shipped -- the "stock PyTorch on the same B200" bar
 """
@@ -233,6 +234,14 @@ def comparators(args):
                                  "sample": f"1 env x {args.agents} agents x 3 steps, {dt:.1f} s; one act() per env per step, OpenMP "
                                            f"pinned to 1 thread by ObservationGenerator (observation_generator.h:115), as shipped"}
         torch.set_num_threads(cores)
+        try:    # the reference's own scaling model: one single-thread worker process per core, one env each (BASELINE.md 4.5 "ref-fair")
+            from oracle import ref_runtime
+            v, secs = ref_runtime.time_fair_processes(args.model, args.map, args.agents, cores, 3)
+            out["cpu_fair_processes"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                         "sample": f"{cores} worker processes x 1 env x {args.agents} agents x 3 steps, {secs:.1f} s; one act() per "
+                                                   f"step and one thread per process (the toolbox's num_process model)"}
+        except Exception as ex:
+            out["cpu_fair_processes"] = {"error": f"{type(ex).__name__}: {ex}"}
         sg = {"unit": UNIT, "kind": "reference", "device": "cuda:0",
               "what": "unmodified reference MAPFGPTInference(device='cuda').act_batch: host tokenizer (1 thread) + stock PyTorch "
                       "forward (SDPA) + torch.multinomial, 2048-row chunks (inference.py:87-101)"}

@@ -168,3 +168,62 @@ def time_rollout(r: ReferenceRollout, steps: int, warmup: int = 1):
         torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return r.E * r.n * steps / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------ "ref-fair": the reference's own
+# scaling model -- `num_process` worker processes (eval_configs/*/0*.yaml: parallel_backend balanced_dask, num_process), each
+# running whole episodes through one act() per step on ONE thread.  Plain subprocesses with hard
+# timeouts (a worker that fails to start must not hang the bench): every worker warms up, reports ready, waits for the go file.
+def _fair_worker_main(argv):
+    import torch
+    worker, model, map_name, agents, steps, sync_dir = int(argv[0]), argv[1], argv[2], int(argv[3]), int(argv[4]), Path(argv[5])
+    sys.path.insert(0, str(ROOT))
+    from mapf_gpt_b200 import maps, weights as W
+    torch.set_num_threads(1)
+    cfg = W.model_config(model)
+    sd = W.random_init(cfg, 1234)
+    m = maps.load_map(map_name)
+    st, gl = maps.sample_instance(m, agents, 0, worker)
+    r = ReferenceRollout(m["grid"], st[None], gl[None], sd, cfg, device="cpu", mode="act")
+    r.step()                                   # warm-up (also builds the generator, which pins OpenMP to one thread)
+    (sync_dir / f"ready_{worker}").touch()
+    deadline = time.time() + 300
+    while not (sync_dir / "go").exists():
+        if time.time() > deadline:
+            raise SystemExit(3)
+        time.sleep(0.002)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r.step()
+    print(f"FAIR_SECONDS {time.perf_counter() - t0:.6f}", flush=True)
+
+
+def time_fair_processes(model: str, map_name: str, agents: int, procs: int, steps: int, timeout_s: float = 240.0):
+    """-> (agent-steps/s summed over `procs` concurrent single-thread workers, slowest worker's seconds)."""
+    import subprocess
+    with tempfile.TemporaryDirectory() as d:
+        ps = [subprocess.Popen([sys.executable, str(Path(__file__).resolve()), "--fair-worker", str(i), model, map_name, str(agents),
+                                str(steps), d], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=str(ROOT))
+              for i in range(procs)]
+        try:
+            t_end = time.time() + timeout_s
+            while sum((Path(d) / f"ready_{i}").exists() for i in range(procs)) < procs:
+                if time.time() > t_end or any(p.poll() not in (None, 0) for p in ps):
+                    raise RuntimeError("a fair-baseline worker did not start")
+                time.sleep(0.05)
+            (Path(d) / "go").touch()
+            secs = []
+            for p in ps:
+                out, _ = p.communicate(timeout=max(1.0, t_end - time.time()))
+                secs.append(float([l for l in out.splitlines() if l.startswith("FAIR_SECONDS")][-1].split()[1]))
+        finally:
+            for p in ps:
+                if p.poll() is None:
+                    p.kill()
+    return procs * agents * steps / max(secs), max(secs)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--fair-worker":
+        sys.path.insert(0, str(ROOT))
+        _fair_worker_main(sys.argv[2:])
