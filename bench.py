@@ -19,9 +19,10 @@ POGEMA soft step.
                  (256 agents x 256 envs), two C5 points (8 and 512 agents on a Berlin tile, 85M) and C1 as the latency of
                  MAPFGPTInference.act() (32 agents x 1 env, obs dicts in, list out, median of 60 calls)
   cpu_baseline   the UNMODIFIED reference (mapf_gpt/inference.py + model.py + compiled generator from baseline/_ref,
-                 oracle/ref_runtime.py) on the host cores: act_batch with all torch threads ("fair");
-  cpu_as_shipped the same through one act() per env with OpenMP pinned to one thread by the generator (as shipped);
-  cpu_fair_processes: one such single-thread worker process per host core, the reference's own scaling model (num_process)
+                 oracle/ref_runtime.py) on the host cores in the form that uses them best: its own scaling model, one single-thread
+                 worker process per core, one env each, one act() per step (= what --impl reference times);
+  cpu_act_batch_threads: one process, act_batch over 8 envs, torch on all threads;
+  cpu_as_shipped one process, one act() per env, OpenMP pinned to one thread by the generator (as shipped)
   stock_gpu      the same reference object with device='cuda' (inference.py:58-60): stock PyTorch fp32 kernels and a
                  bf16-autocast variant, tokenizer on the host as shipped -- the "stock PyTorch on the same B200" bar
 """
@@ -190,19 +191,26 @@ def time_steps(r, steps, warmup, cuda=False):
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (rank 0 only), in the form
+    that uses the cores best: its own scaling model, one single-thread worker process per core, each stepping one env through
+    act() (eval_configs: num_process workers); the oracle port with torch threads when baseline/_ref is missing."""
     if rank != 0:
         return
     import torch
+    from oracle import ref_runtime
     cores = os.cpu_count() or 1
-    envs = args.ref_envs
-    r, kind = make_reference_rollout(args.model, args.map, args.agents, envs, "cpu", "act_batch", cores)
-    dt = time_steps(r, args.steps, args.warmup)
-    val = envs * args.agents * args.steps / dt
-    what = ("unmodified mapf_gpt/inference.py + model.py + compiled observation generator (baseline/_ref), act_batch over the "
-            "sample's envs" if kind == "reference" else "oracle port: compiled/C tokenizer + torch-fp32 forward")
-    sample = (f"{envs} envs x {args.agents} agents x {args.steps} steps of the same workload; {what}; torch fp32 on {cores} "
-              f"threads; env = C soft-step (pogema not installable)")
+    if ref_runtime.available():
+        val, secs = ref_runtime.time_fair_processes(args.model, args.map, args.agents, cores, args.steps, timeout_s=600, warmup=max(args.warmup, 1))
+        kind, envs, dt = "reference", cores, secs
+        what = (f"unmodified mapf_gpt/inference.py + model.py + compiled observation generator (baseline/_ref): {cores} worker processes "
+                f"(the reference's num_process model), one env and one torch thread each, one act() per step")
+    else:
+        envs = args.ref_envs
+        r, kind = make_reference_rollout(args.model, args.map, args.agents, envs, "cpu", "act_batch", cores)
+        dt = time_steps(r, args.steps, args.warmup)
+        val = envs * args.agents * args.steps / dt
+        what = f"oracle port: compiled/C tokenizer + torch-fp32 forward on {cores} threads"
+    sample = (f"{envs} envs x {args.agents} agents x {args.steps} steps of the same workload; {what}; env = C soft-step (pogema not installable)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -222,11 +230,22 @@ def comparators(args):
     envs = args.ref_envs
     r, kind = make_reference_rollout(args.model, args.map, args.agents, envs, "cpu", "act_batch", cores)
     dt = time_steps(r, args.cpu_steps, 1)
-    out["cpu_baseline"] = {"value": envs * args.agents * args.cpu_steps / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                           "sample": f"{envs} envs x {args.agents} agents x {args.cpu_steps} steps of the same workload, {dt:.1f} s; "
-                                     f"{'unmodified reference MAPFGPTInference.act_batch (baseline/_ref)' if kind == 'reference' else 'oracle port'}"
-                                     f", torch fp32 on {cores} threads (re-enabled after the generator pins OpenMP to 1), C soft-step env"}
+    threads = {"value": envs * args.agents * args.cpu_steps / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{envs} envs x {args.agents} agents x {args.cpu_steps} steps of the same workload, {dt:.1f} s; "
+                         f"{'unmodified reference MAPFGPTInference.act_batch (baseline/_ref)' if kind == 'reference' else 'oracle port'}"
+                         f", ONE process, torch fp32 on {cores} threads (re-enabled after the generator pins OpenMP to 1), C soft-step env"}
+    out["cpu_baseline"] = threads
     if kind == "reference":
+        out["cpu_act_batch_threads"] = threads
+        try:    # the reference's own scaling model: one single-thread worker process per core, one env each (BASELINE.md 4.5 "ref-fair")
+            from oracle import ref_runtime
+            v, secs = ref_runtime.time_fair_processes(args.model, args.map, args.agents, cores, 5)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                   "sample": f"{cores} worker processes x 1 env x {args.agents} agents x 5 steps of the same workload, {secs:.1f} s; "
+                                             f"unmodified reference (baseline/_ref), one act() per step and one torch thread per process (its "
+                                             f"own num_process scaling model: the fastest way it uses the host cores), C soft-step env"}
+        except Exception as ex:
+            out["cpu_fair_processes_error"] = f"{type(ex).__name__}: {ex}"
         r, _ = make_reference_rollout(args.model, args.map, args.agents, 1, "cpu", "act", None)
         torch.set_num_threads(1)
         dt = time_steps(r, 3, 1)
@@ -234,14 +253,6 @@ def comparators(args):
                                  "sample": f"1 env x {args.agents} agents x 3 steps, {dt:.1f} s; one act() per env per step, OpenMP "
                                            f"pinned to 1 thread by ObservationGenerator (observation_generator.h:115), as shipped"}
         torch.set_num_threads(cores)
-        try:    # the reference's own scaling model: one single-thread worker process per core, one env each (BASELINE.md 4.5 "ref-fair")
-            from oracle import ref_runtime
-            v, secs = ref_runtime.time_fair_processes(args.model, args.map, args.agents, cores, 3)
-            out["cpu_fair_processes"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                                         "sample": f"{cores} worker processes x 1 env x {args.agents} agents x 3 steps, {secs:.1f} s; one act() per "
-                                                   f"step and one thread per process (the toolbox's num_process model)"}
-        except Exception as ex:
-            out["cpu_fair_processes"] = {"error": f"{type(ex).__name__}: {ex}"}
         sg = {"unit": UNIT, "kind": "reference", "device": "cuda:0",
               "what": "unmodified reference MAPFGPTInference(device='cuda').act_batch: host tokenizer (1 thread) + stock PyTorch "
                       "forward (SDPA) + torch.multinomial, 2048-row chunks (inference.py:87-101)"}

@@ -177,6 +177,7 @@ def time_rollout(r: ReferenceRollout, steps: int, warmup: int = 1):
 def _fair_worker_main(argv):
     import torch
     worker, model, map_name, agents, steps, sync_dir = int(argv[0]), argv[1], argv[2], int(argv[3]), int(argv[4]), Path(argv[5])
+    warmup = int(argv[6]) if len(argv) > 6 else 1
     sys.path.insert(0, str(ROOT))
     from mapf_gpt_b200 import maps, weights as W
     torch.set_num_threads(1)
@@ -185,7 +186,8 @@ def _fair_worker_main(argv):
     m = maps.load_map(map_name)
     st, gl = maps.sample_instance(m, agents, 0, worker)
     r = ReferenceRollout(m["grid"], st[None], gl[None], sd, cfg, device="cpu", mode="act")
-    r.step()                                   # warm-up (also builds the generator, which pins OpenMP to one thread)
+    for _ in range(max(warmup, 1)):            # warm-up (also builds the generator, which pins OpenMP to one thread)
+        r.step()
     (sync_dir / f"ready_{worker}").touch()
     deadline = time.time() + 300
     while not (sync_dir / "go").exists():
@@ -198,12 +200,12 @@ def _fair_worker_main(argv):
     print(f"FAIR_SECONDS {time.perf_counter() - t0:.6f}", flush=True)
 
 
-def time_fair_processes(model: str, map_name: str, agents: int, procs: int, steps: int, timeout_s: float = 240.0):
+def time_fair_processes(model: str, map_name: str, agents: int, procs: int, steps: int, timeout_s: float = 240.0, warmup: int = 1):
     """-> (agent-steps/s summed over `procs` concurrent single-thread workers, slowest worker's seconds)."""
     import subprocess
     with tempfile.TemporaryDirectory() as d:
         ps = [subprocess.Popen([sys.executable, str(Path(__file__).resolve()), "--fair-worker", str(i), model, map_name, str(agents),
-                                str(steps), d], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=str(ROOT))
+                                str(steps), d, str(warmup)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=str(ROOT))
               for i in range(procs)]
         try:
             t_end = time.time() + timeout_s
