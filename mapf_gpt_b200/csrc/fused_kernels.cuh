@@ -102,8 +102,11 @@ template <int V> struct IntC { static constexpr int value = V; };
 // the thread's HALF columns in batches of <= 48: one TMEM round trip per batch instead of one per 16 columns
 #define MG_COL_BATCHES(HALF_, F)                                                 \
     do {                                                                         \
-        static_assert((HALF_) == 80 || (HALF_) == 128, "column batches");        \
-        if constexpr ((HALF_) == 80) {                                           \
+        static_assert((HALF_) == 64 || (HALF_) == 80 || (HALF_) == 128, "column batches"); \
+        if constexpr ((HALF_) == 64) {                                           \
+            F(IntC<0>{}, IntC<32>{});                                            \
+            F(IntC<32>{}, IntC<32>{});                                           \
+        } else if constexpr ((HALF_) == 80) {                                    \
             F(IntC<0>{}, IntC<48>{});                                            \
             F(IntC<48>{}, IntC<32>{});                                           \
         } else {                                                                 \
@@ -149,10 +152,19 @@ struct PostAttnCfg {
     static constexpr int CTAS_PER_SM = (NT == 1 && C <= 160) ? 2 : 1;
     static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
-    static constexpr int THREADS = 64 + 256 * NT;
+    // NH column groups per tile: a tile's 128 rows are covered by 4 warps (TMEM lane quadrants) x NH groups of C / NH columns.
+    // C = 256 runs one CTA per SM (TMEM / shared memory) at 16 % warps-active with its 8 worker warps; 16 worker warps (NH = 4,
+    // -DMG_POST_NH256=4) were measured SLOWER, 3.69 -> 4.06 ms per launch: twice the barrier arrivals and TMEM round trips per
+    // phase for half the work per thread (profiles/r02_experiments.md).  Default: 2 column groups everywhere.
+#ifndef MG_POST_NH256
+#define MG_POST_NH256 2
+#endif
+    static constexpr int NH = (C == 256 && NT == 1) ? MG_POST_NH256 : 2;
+    static constexpr int NW = 4 * NH;                // worker warps per tile
+    static constexpr int THREADS = 64 + 32 * NW * NT;
     static constexpr int QKV_STAGES = 6 * NFC / U;     // next block's c_attn: 6 half n-tiles of HC columns (FC-chunk stage format)
     static constexpr int NBAR = 3 * STAGES + 2 + NT * 14;
-    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * SLOT_BYTES + NT * 4 * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
+    static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * SLOT_BYTES + NT * 2 * NH * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
     static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
     static_assert(TMEM_COLS <= 512, "post_attn_kernel: TMEM budget");
@@ -181,19 +193,20 @@ post_attn_kernel(const PostAttnArgs a)
     using K = PostAttnCfg<C, NT, UU, CL>;
     constexpr int HC = K::HC, S = K::STAGES, U = K::U;
     constexpr bool PAIR = CL == 2;
-    constexpr int WARR = 8 * CL;              // arrivals on a worker -> issuer barrier: one per worker warp of the CTA group
+    constexpr int NH = K::NH, NW = K::NW;     // column groups / worker warps per tile
+    constexpr int WARR = NW * CL;             // arrivals on a worker -> issuer barrier: one per worker warp of the CTA group
     constexpr int CB = C / CL, HB = HC / CL;  // weight rows per CTA of a C-wide / HC-wide B operand
     constexpr int UNIT_B = K::UNIT_BYTES / CL;
     constexpr uint32_t UM = 128 * CL;         // UMMA M
-    constexpr int PROD_WARP = 8 * NT, MMA_WARP = 8 * NT + 1;
+    constexpr int PROD_WARP = NW * NT, MMA_WARP = NW * NT + 1;
     const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = crank == 0;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *As = smem;                                   // [NT] A tiles
     uint8_t *Hs = As + NT * K::A_BYTES;                   // [NT] hidden-chunk buffers
     uint8_t *ring = Hs + NT * K::H_BYTES;
-    float *red = reinterpret_cast<float *>(ring + S * K::SLOT_BYTES);    // [NT][2 kinds][2 halves][128]
-    uint64_t *full = reinterpret_cast<uint64_t *>(red + NT * 4 * 128);
+    float *red = reinterpret_cast<float *>(ring + S * K::SLOT_BYTES);    // [NT][2 kinds][NH column groups][128]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + NT * 2 * NH * 128);
     uint64_t *empty = full + S;
     uint64_t *pfull = empty + S;         // leader only: the peer's half of the stage landed (relayed)
     uint64_t *bar_proj = pfull + S;      // proj UMMAs retired (all tiles)
@@ -254,10 +267,10 @@ post_attn_kernel(const PostAttnArgs a)
             bulk_g2s(ring + i * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[i]);
         }
     }
-    constexpr int HALF = C / 2;                           // residual columns handled by one worker thread
+    constexpr int HALF = C / NH;                          // residual columns handled by one worker thread
     float4 xv[HALF / 4];                                  // this thread's residual columns
     auto load_x = [&](int mtl) {
-        const int row = (warp & 3) * 32 + lane, hh = (warp >> 2) & 1;
+        const int row = (warp & 3) * 32 + lane, hh = (warp % NW) >> 2;
         if (a.tab0 != nullptr) {   // block 0: this thread's 2C contiguous bytes of its token's record (L2-resident table)
             const int tok = min((int)a.tokens0[(size_t)mtl * 128 + row], 66);
             const float4 *src = reinterpret_cast<const float4 *>(a.tab0 + ((size_t)tok * 256 + ((mtl & 1) << 7) + row) * a.tab_nrec) + hh * (HALF / 4);
@@ -270,7 +283,7 @@ post_attn_kernel(const PostAttnArgs a)
         }
     };
     if constexpr (!PERSIST) {   // the residual tile is on its way to registers during the rendezvous
-        if (warp < 8 * NT) load_x(mt0 + (warp >> 3));
+        if (warp < NW * NT) load_x(mt0 + warp / NW);
     }
     if (threadIdx.x == 0) {
         mbar_init(bar_proj, 1);
@@ -524,12 +537,12 @@ post_attn_kernel(const PostAttnArgs a)
         }
     } else {
         // ------------------------------------------------------------------ workers (256 threads per tile)
-        const int t = warp >> 3;                          // tile of this worker
-        const int q = warp & 3, h = (warp >> 2) & 1;
+        const int t = warp / NW;                          // tile of this worker
+        const int q = warp & 3, h = (warp % NW) >> 2;     // TMEM lane quadrant, column group
         const int r = q * 32 + lane;
         const uint32_t trow = tmem + t * K::TILE_COLS + ((uint32_t)(q * 32) << 16);
         uint8_t *At = As + t * K::A_BYTES;
-        float *red_s = red + t * 512, *red_q = red_s + 256;
+        float *red_s = red + t * (2 * NH * 128), *red_q = red_s + NH * 128;
         const float inv_c = 1.0f / (float)C;
         const uint32_t nb = 1 + t;                        // named barrier of this tile's 256 workers
         MG_LAP_INIT;
@@ -590,9 +603,15 @@ post_attn_kernel(const PostAttnArgs a)
                 red_s[h * 128 + r] = s0 + s1;
                 red_q[h * 128 + r] = q0 + q1;
             }
-            named_bar_sync(nb, 256);
-            const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
-            const float var = fmaxf((red_q[r] + red_q[128 + r]) * inv_c - mean * mean, 0.f);
+            named_bar_sync(nb, 128 * NH);
+            float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+            for (int g2 = 0; g2 < NH; g2++) {
+                ssum += red_s[g2 * 128 + r];
+                qsum += red_q[g2 * 128 + r];
+            }
+            const float mean = ssum * inv_c;
+            const float var = fmaxf(qsum * inv_c - mean * mean, 0.f);
             const float rstd = rsqrtf(var + 1e-5f);
             const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
             auto norm = [&](auto c0_, auto n_) {
@@ -613,7 +632,7 @@ post_attn_kernel(const PostAttnArgs a)
         }
 
         // ---- MLP chunks: acc1 -> GELU -> hidden chunk in smem
-        constexpr int HH = HC / 2;            // hidden columns per thread per chunk
+        constexpr int HH = HC / NH;           // hidden columns per thread per chunk
         constexpr int NV = HH / 8;            // 16-byte groups
         uint8_t *Hb = Hs + t * K::H_BYTES;
         // (Issuing the TMEM reads of chunk j+1 before chunk j's hidden values are stored -- a register ping-pong software
@@ -680,7 +699,7 @@ post_attn_kernel(const PostAttnArgs a)
             if (a.xn_out != nullptr || fuse_qkv) {
                 // the scratch was last read in the LN2 epilogue; every worker has long passed that point (the mbarrier chain of
                 // the MLP phase orders it), the barrier states it in a form compute-sanitizer's racecheck can follow
-                named_bar_sync(nb, 256);
+                named_bar_sync(nb, 128 * NH);
                 {
                     float s0, s1, q0, q1;
                     upk2(sum2, s0, s1);
@@ -688,9 +707,15 @@ post_attn_kernel(const PostAttnArgs a)
                     red_s[h * 128 + r] = s0 + s1;
                     red_q[h * 128 + r] = q0 + q1;
                 }
-                named_bar_sync(nb, 256);
-                const float mean = (red_s[r] + red_s[128 + r]) * inv_c;
-                const float var = fmaxf((red_q[r] + red_q[128 + r]) * inv_c - mean * mean, 0.f);
+                named_bar_sync(nb, 128 * NH);
+                float ssum = 0.f, qsum = 0.f;
+#pragma unroll
+                for (int g2 = 0; g2 < NH; g2++) {
+                    ssum += red_s[g2 * 128 + r];
+                    qsum += red_q[g2 * 128 + r];
+                }
+                const float mean = ssum * inv_c;
+                const float var = fmaxf(qsum * inv_c - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + 1e-5f);
                 const f32x2 la = pk2(rstd, rstd), lb = pk2(-mean * rstd, -mean * rstd);
                 if (fuse_qkv) {
@@ -731,25 +756,25 @@ post_attn_kernel(const PostAttnArgs a)
 #pragma unroll 1
             for (int hh = 0; hh < 6; hh++) {
                 const int buf = hh % 3;
-                const uint32_t col = (buf == 0 ? C : (buf == 1 ? 0 : HC)) + h * (HC / 2);
+                const uint32_t col = (buf == 0 ? C : (buf == 1 ? 0 : HC)) + h * (HC / NH);
                 mbar_wait(&bar_qf[t * 3 + buf], (hh / 3) & 1);
                 tc_fence_after();
                 MG_WLAP(11);  // waiting for a q/k/v half-tile
                 if (threadIdx.x == 0) MG_STAMP(94 + hh);
-                uint32_t v[HC / 2];
+                uint32_t v[HC / NH];
 #pragma unroll
-                for (int c = 0; c < HC / 2; c += 8) tmem_ld8(trow + col + c, *reinterpret_cast<uint32_t(*)[8]>(&v[c]));
+                for (int c = 0; c < HC / NH; c += 8) tmem_ld8(trow + col + c, *reinterpret_cast<uint32_t(*)[8]>(&v[c]));
                 tmem_wait_ld();
                 tc_fence_before();
                 arrive_issuer(&bar_qe[t * 3 + buf]);   // values are in registers: the issuer may reuse the buffer
 #pragma unroll
-                for (int j = 0; j < HC / 16; j++) {
+                for (int j = 0; j < HC / NH / 8; j++) {
                     uint4 o;
                     o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
                     o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
                     o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
                     o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                    __stcs(&Oseq[qkv_off[(hh * HC + h * (HC / 2)) / 8 + j]], o);   // streaming: 3.4 GB per launch pass through L2 once
+                    __stcs(&Oseq[qkv_off[(hh * HC + h * (HC / NH)) / 8 + j]], o);   // streaming: 3.4 GB per launch pass through L2 once
                 }
                 MG_WLAP(12);  // q/k/v half-tile -> HBM
             }
@@ -759,7 +784,7 @@ post_attn_kernel(const PostAttnArgs a)
             MG_WLAP(13);
             break;
         }
-        if (g + gstride < n_groups) named_bar_sync(nb, 256);
+        if (g + gstride < n_groups) named_bar_sync(nb, 128 * NH);
         MG_WLAP(13);
         }   // tile groups
     }
