@@ -223,10 +223,13 @@ static int upload_packed_pair(const float *W, int N, int K, int BN, __nv_bfloat1
 static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const float *Wproj2, const float *Wqkv_next,
                                    const float *g2, const float *gn, int C, int split, float qscale, __nv_bfloat16 **out)
 {
-    const int HC = C / 2, NCH = 8, NPROJ = C / 16, NFC = C / 32, NP2 = HC / 16;
+    // PostAttnCfg<C>::WIDE (C = 256): the MLP runs in 4 chunks of C hidden columns (FC units = one k-step of all C rows, like
+    // proj) instead of 8 chunks of C/2; the c_attn tail keeps the narrow half-n-tile format either way
+    const bool wide = PostAttnCfg<256, 1, 0, 1>::WIDE && C == 256;
+    const int HC = C / 2, HM = wide ? C : HC, NCH = 4 * C / HM, NPROJ = C / 16, NFC = C / 32, NFCM = wide ? C / 16 : C / 32, NP2 = HM / 16;
     const int U = C == 160 ? 5 : 4;              // units per stage (PostAttnCfg::U)
     const size_t stage_elems = (size_t)16 * C;   // 32*C bytes per unit
-    const size_t total = (size_t)(NPROJ + NCH * (NFC + NP2) + (Wqkv_next ? 6 * NFC : 0)) * stage_elems;
+    const size_t total = (size_t)(NPROJ + NCH * (NFCM + NP2) + (Wqkv_next ? 6 * NFC : 0)) * stage_elems;
     std::vector<uint16_t> h(total, 0);
     size_t st = 0;
     auto put_kn = [&](size_t base, int kc, int rows, int n, int k8, float v) {   // [kc][rows][8]; base = unit index * stage_elems
@@ -242,6 +245,13 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
         for (int n = 0; n < C; n++)
             for (int k = 0; k < 16; k++) put_kn(st * stage_elems, k / 8, C, n, k % 8, Wproj[(size_t)n * C + ks * 16 + k]);
     auto put_fc = [&](int j) {
+        if (wide) {   // one k-step (16 k) of the chunk's C hidden rows per unit
+            for (int ks = 0; ks < NFCM; ks++, st++)
+                for (int n = 0; n < C; n++)
+                    for (int k = 0; k < 16; k++)
+                        put_kn(st * stage_elems, k / 8, C, n, k % 8, Wfc[(size_t)(j * C + n) * C + ks * 16 + k] * g2[ks * 16 + k]);
+            return;
+        }
         for (int kb = 0; kb < NFC; kb++, st++)
             for (int n = 0; n < HC; n++)
                 for (int k = 0; k < 32; k++)
@@ -251,7 +261,7 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
         for (int ks = 0; ks < NP2; ks++, st++)
             for (int n = 0; n < C; n++)
                 for (int k = 0; k < 16; k++)
-                    put_kn(st * stage_elems, k / 8, C, n, k % 8, Wproj2[(size_t)n * 4 * C + j * HC + ks * 16 + k]);
+                    put_kn(st * stage_elems, k / 8, C, n, k % 8, Wproj2[(size_t)n * 4 * C + j * HM + ks * 16 + k]);
     };
     put_fc(0);
     for (int j = 0; j < NCH; j++) {

@@ -136,21 +136,30 @@ __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean,
 //   * LayerNorm statistics are single-pass (sum, sum of squares) in packed fp32x2.
 template <int C, int NT, int UU = 0, int CL = 1>
 struct PostAttnCfg {
-    static constexpr int HC = C / 2;                 // hidden chunk (FC N, proj2 K per chunk)
-    static constexpr int NCH = 4 * C / HC;           // 8 chunks
+    // WIDE (C = 256 only, -DMG_POST_WIDE256=1): the MLP in 4 chunks of C hidden columns instead of 8 of C/2 -- half the phase
+    // hand-offs per tile (TMEM 256 + 256 = 512 columns, hidden buffer 64 KB); the c_attn tail keeps half n-tiles of HC columns.
+    // Measured SLOWER (3.62 -> 3.70 ms per launch: coarser chunks overlap the tensor pipe and the workers less): off by default.
+#ifndef MG_POST_WIDE256
+#define MG_POST_WIDE256 0
+#endif
+    static constexpr bool WIDE = C == 256 && NT == 1 && MG_POST_WIDE256;
+    static constexpr int HC = C / 2;                 // half n-tile of the fused c_attn; MLP chunk width unless WIDE
+    static constexpr int HM = WIDE ? C : HC;         // hidden chunk (FC N, proj2 K per chunk)
+    static constexpr int NCH = 4 * C / HM;           // 8 chunks (4 when WIDE)
     static constexpr int UNIT_BYTES = 32 * C;        // [2 kc][C][16B] == [4 kc][HC][16B]
     static constexpr int NPROJ = C / 16;             // units of the proj GEMM (one k-step each)
-    static constexpr int NFC = C / 32;               // units per FC chunk (two k-steps each)
-    static constexpr int NP2 = HC / 16;              // units per proj2 chunk (one k-step each)
+    static constexpr int NFCQ = C / 32;              // units per half n-tile of the fused c_attn (two k-steps each)
+    static constexpr int NFC = WIDE ? C / 16 : C / 32;   // units per FC chunk (two k-steps of HC rows each; WIDE: one k-step of C rows)
+    static constexpr int NP2 = HM / 16;              // units per proj2 chunk (one k-step each)
     static constexpr int U = UU ? UU : (C == 160 ? 5 : 4);   // units per stage
     static constexpr int STAGE_BYTES = U * UNIT_BYTES;
     static constexpr int TOTAL_STAGES = (NPROJ + NCH * (NFC + NP2)) / U;
     static constexpr int A_BYTES = C * 256;          // [C/8][128][16B] per tile
-    static constexpr int H_BYTES = HC * 256;         // [HC/8][128][16B] per tile
+    static constexpr int H_BYTES = HM * 256;         // [HM/8][128][16B] per tile
     static constexpr int SLOT_BYTES = STAGE_BYTES / CL;   // CTA pair: each CTA holds its half (N/2 weight rows) of every stage
-    static constexpr int STAGES = CL * (UU ? (NT == 2 ? 4 : (C <= 160 ? 2 : 3)) * (C == 160 ? 5 : 4) / UU : (NT == 2 ? 4 : (C <= 160 ? 2 : 3)));
+    static constexpr int STAGES = CL * (UU ? (NT == 2 ? 4 : (C <= 160 ? 2 : 3)) * (C == 160 ? 5 : 4) / UU : (NT == 2 ? 4 : (C <= 160 || WIDE ? 2 : 3)));
     static constexpr int CTAS_PER_SM = (NT == 1 && C <= 160) ? 2 : 1;
-    static constexpr int TILE_COLS = (C + HC) <= 256 ? 256 : 512;          // TMEM columns per tile
+    static constexpr int TILE_COLS = (C + HM) <= 256 ? 256 : 512;          // TMEM columns per tile
     static constexpr uint32_t TMEM_COLS = TILE_COLS * NT;
     // NH column groups per tile: a tile's 128 rows are covered by 4 warps (TMEM lane quadrants) x NH groups of C / NH columns.
     // C = 256 runs one CTA per SM (TMEM / shared memory) at 16 % warps-active with its 8 worker warps; 16 worker warps (NH = 4,
@@ -162,11 +171,11 @@ struct PostAttnCfg {
     static constexpr int NH = (C == 256 && NT == 1) ? MG_POST_NH256 : 2;
     static constexpr int NW = 4 * NH;                // worker warps per tile
     static constexpr int THREADS = 64 + 32 * NW * NT;
-    static constexpr int QKV_STAGES = 6 * NFC / U;     // next block's c_attn: 6 half n-tiles of HC columns (FC-chunk stage format)
+    static constexpr int QKV_STAGES = 6 * NFCQ / U;    // next block's c_attn: 6 half n-tiles of HC columns (narrow FC-chunk stage format)
     static constexpr int NBAR = 3 * STAGES + 2 + NT * 14;
     static constexpr int SMEM_BYTES = NT * (A_BYTES + H_BYTES) + STAGES * SLOT_BYTES + NT * 2 * NH * 128 * 4 + NBAR * 8 + 16 + (3 * C / 8) * 4;
     static_assert(C % 32 == 0 && C <= 256, "post_attn_kernel: C must be a multiple of 32, <= 256");
-    static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0, "stage size must divide every GEMM phase");
+    static_assert(NPROJ % U == 0 && NFC % U == 0 && NP2 % U == 0 && NFCQ % U == 0, "stage size must divide every GEMM phase");
     static_assert(TMEM_COLS <= 512, "post_attn_kernel: TMEM budget");
     static_assert(CL == 1 || (CL == 2 && NT == 1 && C % 32 == 0), "CTA pairs: one tile per CTA, N/2 a multiple of 16");
 };
@@ -445,6 +454,12 @@ post_attn_kernel(const PostAttnArgs a)
                             tc_fence_after();
                         }
                         if (elect_one()) {
+                            if constexpr (K::WIDE) {   // one k-step of all C hidden columns of the chunk per unit (proj's unit format)
+#pragma unroll
+                                for (int u = 0; u < U; u++)
+                                    mma(tmem + t * K::TILE_COLS + C, umma_desc(a_addr + t * K::A_BYTES + (st * U + u) * 4096, 2048, 128),
+                                        umma_desc(b + u * UNIT_B, CB * 16, 128), idescC, (st | u) != 0);
+                            } else {
 #pragma unroll
                             for (int u = 0; u < U; u++)
 #pragma unroll
@@ -453,6 +468,7 @@ post_attn_kernel(const PostAttnArgs a)
                                         umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
                                         umma_desc(b + u * UNIT_B + ks * 2 * (HB * 16), HB * 16, 128), idescH,
                                         (st | u | ks) != 0);
+                            }
                             if (st == K::NFC / U - 1) commit(&bar_a1f[t]);
                             if (t == NT - 1) {
                                 commit(&empty[i % S]);
@@ -504,7 +520,7 @@ post_attn_kernel(const PostAttnArgs a)
                 for (int hh = 0; hh < 6; hh++) {
                     const int buf = hh % 3;
                     const uint32_t col = buf == 0 ? C : (buf == 1 ? 0 : HC);
-                    for (int st = 0; st < K::NFC / U; st++, i++) {
+                    for (int st = 0; st < K::NFCQ / U; st++, i++) {
                         const uint32_t b = stage_wait(i);
 #pragma unroll
                         for (int t = 0; t < NT; t++) {
@@ -521,7 +537,7 @@ post_attn_kernel(const PostAttnArgs a)
                                             umma_desc(a_addr + t * K::A_BYTES + ((st * U + u) * 2 + ks) * 4096, 2048, 128),
                                             umma_desc(b + u * UNIT_B + ks * 2 * (HB * 16), HB * 16, 128), idescH,
                                             (st | u | ks) != 0);
-                                if (st == K::NFC / U - 1) commit(&bar_qf[t * 3 + buf]);
+                                if (st == K::NFCQ / U - 1) commit(&bar_qf[t * 3 + buf]);
                                 if (t == NT - 1) commit(&empty[i % S]);
                             }
                             __syncwarp();
@@ -632,8 +648,11 @@ post_attn_kernel(const PostAttnArgs a)
         }
 
         // ---- MLP chunks: acc1 -> GELU -> hidden chunk in smem
-        constexpr int HH = HC / NH;           // hidden columns per thread per chunk
-        constexpr int NV = HH / 8;            // 16-byte groups
+        constexpr int HH = K::HM / NH;        // hidden columns per thread per chunk
+        constexpr int SB = HH > 64 ? 64 : HH; // ... drained / activated / stored in sub-batches of SB columns (registers)
+        constexpr int NSUB = HH / SB;
+        constexpr int NV = SB / 8;            // 16-byte groups per sub-batch
+        static_assert(HH % SB == 0 && SB % 8 == 0, "MLP chunk sub-batches");
         uint8_t *Hb = Hs + t * K::H_BYTES;
         // (Issuing the TMEM reads of chunk j+1 before chunk j's hidden values are stored -- a register ping-pong software
         // pipeline -- was measured SLOWER, 2.18 vs 1.80 ms per launch: it needs 40 more live registers under the 96-register
@@ -644,27 +663,34 @@ post_attn_kernel(const PostAttnArgs a)
             tc_fence_after();
             MG_WLAP(3);  // waiting for the FC chunk
             if (threadIdx.x == 0) MG_STAMP(60 + 3 * j);
-            uint32_t v[NV][8];
 #pragma unroll
-            for (int g = 0; g < NV; g++) tmem_ld8(trow + C + h * HH + g * 8, v[g]);
-            tmem_wait_ld();
-            tc_fence_before();
-            arrive_issuer(&bar_a1e[t]);
-            MG_WLAP(4);  // FC chunk -> registers
-            if (threadIdx.x == 0) MG_STAMP(61 + 3 * j);
-            uint4 o[NV];
+            for (int sub = 0; sub < NSUB; sub++) {
+                uint32_t v[NV][8];
 #pragma unroll
-            for (int g = 0; g < NV; g++) {
-                o[g].x = pack_bf16x2_p(gelu2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1])));
-                o[g].y = pack_bf16x2_p(gelu2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3])));
-                o[g].z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
-                o[g].w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
+                for (int g = 0; g < NV; g++) tmem_ld8(trow + C + h * HH + sub * SB + g * 8, v[g]);
+                tmem_wait_ld();
+                if (sub == NSUB - 1) {            // the whole chunk is in registers / already stored: FC(j+1) may overwrite it
+                    tc_fence_before();
+                    arrive_issuer(&bar_a1e[t]);
+                    MG_WLAP(4);  // FC chunk -> registers
+                    if (threadIdx.x == 0) MG_STAMP(61 + 3 * j);
+                }
+                uint4 o[NV];
+#pragma unroll
+                for (int g = 0; g < NV; g++) {
+                    o[g].x = pack_bf16x2_p(gelu2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1])));
+                    o[g].y = pack_bf16x2_p(gelu2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3])));
+                    o[g].z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
+                    o[g].w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
+                }
+                if (sub == NSUB - 1) MG_WLAP(5);  // GELU
+                if (sub == 0 && j >= 1) {
+                    mbar_wait(&bar_he[t], (j - 1) & 1);   // proj2(j-1) has finished reading the buffer
+                    MG_WLAP(6);  // waiting for the hidden buffer
+                }
+#pragma unroll
+                for (int g = 0; g < NV; g++) *reinterpret_cast<uint4 *>(Hb + ((h * (HH / 8) + sub * NV + g) * 128 + r) * 16) = o[g];
             }
-            MG_WLAP(5);  // GELU
-            if (j >= 1) mbar_wait(&bar_he[t], (j - 1) & 1);       // proj2(j-1) has finished reading the buffer
-            MG_WLAP(6);  // waiting for the hidden buffer
-#pragma unroll
-            for (int g = 0; g < NV; g++) *reinterpret_cast<uint4 *>(Hb + ((h * NV + g) * 128 + r) * 16) = o[g];
             fence_proxy_async_smem();
             arrive_issuer(&bar_hf[t]);
             MG_WLAP(7);  // hidden chunk -> smem
