@@ -285,7 +285,7 @@ def comparators(args):
 def kernel_table(model_cfg, ktimes, total_ms, seqs_per_gpu, pk):
     C, T = model_cfg.n_embd, 256
     fused_path = C in (160, 256) and not GENERIC
-    pruned = fused_path and os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1"
+    pruned = os.environ.get("MAPF_GPT_B200_NO_PRUNE") != "1"     # last-block pruning: fused and (since round 2) generic path
     fuse_qkv = fused_path and os.environ.get("MAPF_GPT_B200_NO_QKV_FUSION") is None
     table0 = fuse_qkv and os.environ.get("MAPF_GPT_B200_NO_BLOCK0_TABLE") is None
     chunk = int(os.environ.get("MAPF_GPT_B200_CHUNK_SEQS", "8192")) // 128 * 128

@@ -703,6 +703,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             continue;
         }
         const bool lnf = m.ln_fused;    // ln_1 / ln_2 live in the epilogues of the GEMMs around them; w.XN holds the RAW bf16 residual
+        bool pruned_tail = false;
         prof_begin(e, KC_EMBED);
         embed_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, C, lnf ? w.XN : nullptr, w.STATS);
         prof_end(e);
@@ -717,6 +718,34 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             g.A = w.XN; g.W = L.wqkv; g.Wp = L.wqkv_p; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
             if (lnf) { g.stats_in = w.STATS; g.colsum = L.cs_qkv; }
             if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
+            if (l + 1 == m.cfg.n_layer && e->prune_last && (hs == 32 || hs == 64) && 32 * H <= 512) {
+                // Last block pruned (as on the fused path): only logits[255][0:5] are consumed, so K and V are
+                // needed for all tokens but attention, c_proj and the MLP for token 255 alone.  The tail runs on COMPACT tiles (one
+                // row per sequence) through the single-CTA GEMM with the plain weights and the LayerNorm kernel.
+                prof_begin(e, KC_ATTN_LAST);
+                if (hs == 32) last_attn_kernel<32><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 0.6931471805599453f);
+                else last_attn_kernel<64><<<ns, 32 * H, 0, e->stream>>>(w.QKV, w.X, w.ATTc, w.Xc, H, C, 0.6931471805599453f);
+                prof_end(e);
+                const int Mc = (ns + 127) / 128 * 128;
+                GemmArgs t{};
+                t.A = w.ATTc; t.W = L.wproj; t.out = w.Xc; t.M = Mc; t.N = C; t.K = C;
+                if ((rc = launch_gemm<EPI_RESID>(e, m.BN, t, KC_POST_LAST))) return rc;
+                prof_begin(e, KC_POST_LAST);
+                launch_ln(e, w.Xc, L.ln2, w.XN, C, Mc / 128);
+                prof_end(e);
+                t = GemmArgs{};
+                t.A = w.XN; t.W = L.wfc; t.out = w.HID; t.M = Mc; t.N = 4 * C; t.K = C;
+                if ((rc = launch_gemm<EPI_GELU>(e, m.BN, t, KC_POST_LAST))) return rc;
+                t = GemmArgs{};
+                t.A = w.HID; t.W = L.wproj2; t.out = w.Xc; t.M = Mc; t.N = C; t.K = 4 * C;
+                if ((rc = launch_gemm<EPI_RESID>(e, m.BN, t, KC_POST_LAST))) return rc;
+                prof_begin(e, KC_HEAD);
+                head_compact_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.Xc, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
+                prof_end(e);
+                if (ev) launch_head_loss(e, w.Xc, 1, *ev, s0, ns);
+                pruned_tail = true;
+                break;
+            }
             AttnArgs at{};
             at.qkv = w.QKV; at.out = w.ATT; at.n_head = H; at.C = C;
             at.scale_log2e = 1.0f;   // folded into Wq (Model::q_fold)
@@ -739,6 +768,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             if (lnf && l + 1 < m.cfg.n_layer) { g.xb_out = w.XN; g.stats_out = w.STATS; }   // ... of the next block's ln_1
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ2))) return rc;
         }
+        if (pruned_tail) continue;
         prof_begin(e, KC_HEAD);
         head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.X, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
         prof_end(e);
