@@ -253,8 +253,9 @@ def test_generic_path_kernel_variants_agree(dev, monkeypatch):
     toks = np.random.default_rng(9).integers(0, 67, (66, 256)).astype(np.int8)
     outs = {}
     for name, env in (("default", {}), ("ln_kernel", {"MAPF_GPT_B200_LN_FUSED": "0"}), ("single_cta_gemm", {"MAPF_GPT_B200_GEMM_PAIR": "0"}),
-                      ("smem_p_attention", {"MAPF_GPT_B200_ATTN_CLASSIC": "1", "MAPF_GPT_B200_LN_FUSED": "0"})):
-        for k in ("MAPF_GPT_B200_GEMM_PAIR", "MAPF_GPT_B200_ATTN_CLASSIC", "MAPF_GPT_B200_LN_FUSED"):
+                      ("smem_p_attention", {"MAPF_GPT_B200_ATTN_CLASSIC": "1", "MAPF_GPT_B200_LN_FUSED": "0"}),
+                      ("no_prune", {"MAPF_GPT_B200_NO_PRUNE": "1"})):
+        for k in ("MAPF_GPT_B200_GEMM_PAIR", "MAPF_GPT_B200_ATTN_CLASSIC", "MAPF_GPT_B200_LN_FUSED", "MAPF_GPT_B200_NO_PRUNE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -270,6 +271,8 @@ def test_generic_path_kernel_variants_agree(dev, monkeypatch):
     from oracle import gpt_oracle as G
     ref = G.forward_logits(sd, cfg.n_layer, cfg.n_head, torch.from_numpy(toks.astype(np.int64)))[:, :5].numpy()
     assert np.abs(outs["default"] - ref).max() < LOGIT_TOL and np.abs(outs["ln_kernel"] - ref).max() < LOGIT_TOL
+    # last block in full (every token) vs pruned to token 255 (default): same function, different kernels on the last block
+    assert np.abs(outs["no_prune"] - ref).max() < LOGIT_TOL and np.abs(outs["default"] - outs["no_prune"]).max() < 2 * LOGIT_TOL
 
 
 # ------------------------------------------------------------------------------------------------ large maps
