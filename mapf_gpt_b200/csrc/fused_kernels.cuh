@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(const uint8_t *__restrict
     }
     __syncthreads();
     const int mt = blockIdx.x, r = threadIdx.x;
-    const int tok = tokens[(size_t)mt * 128 + r];
+    const int tok = min((int)tokens[(size_t)mt * 128 + r], 66);   // ids are validated on the host; clamp like block0_lookup
     const float4 *te = reinterpret_cast<const float4 *>(wte_s + tok * pitch);
     const float4 *pe = reinterpret_cast<const float4 *>(wpe_ti) + (size_t)(mt & 1) * (C / 4) * 128 + r;
     float4 *Xo = reinterpret_cast<float4 *>(X) + (size_t)mt * (C / 4) * 128 + r;
