@@ -170,6 +170,9 @@ int mg_engine_set_profiling(mg_engine *e, int on);
 int mg_engine_last_timing(mg_engine *e, float *total_ms, float *phases_ms3);
 /* number of kernels this library launched since creation (bench.py's gpu_launches) */
 long long mg_engine_launch_count(const mg_engine *e);
+/* stream lanes the forward uses when a timestep has more than one chunk (2: attention of one chunk overlaps the post-attention
+ * kernels of the other on the same SMs; per-kernel event timing -- profiling on -- always runs single-lane); DESIGN.md section 4 */
+int mg_engine_num_lanes(const mg_engine *e);
 /* timing of the dominant kernels: name list is fixed, see DESIGN.md */
 int mg_engine_kernel_times(mg_engine *e, float *ms_out, int n);
 

@@ -75,6 +75,7 @@ _SIGS = {
     "mg_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mg_engine_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mg_engine_launch_count": (C.c_longlong, [C.c_void_p]),
+    "mg_engine_num_lanes": (C.c_int, [C.c_void_p]),
     "mg_engine_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "mg_gen_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.POINTER(MgParams)]),
     "mg_gen_create_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -92,6 +92,20 @@ struct Workspace {
 };
 
 struct EvPair { cudaEvent_t a, b; int kc; };
+#ifndef MG_LANES_DEFAULT
+#define MG_LANES_DEFAULT(C) 1
+#endif
+
+// Stream lanes (fused path, C = 160): the forward chunks of one timestep alternate between two lanes, each with its own
+// workspace and two streams -- attention on a HIGH-priority stream, everything else on a low-priority one -- so that the
+// MUFU-bound attention CTAs of one chunk (grid = one per SM) share the SMs with the tensor/FMA-bound post_attn CTAs of the
+// other chunk instead of running back to back (one CTA of each fits per SM: 2 x 115 KB of shared memory, 2 x 256 TMEM columns).
+struct Lane {
+    Workspace ws;
+    cudaStream_t lo = nullptr, hi = nullptr;
+    int *ctr = nullptr;               // work counter of this lane's persistent attention launches
+    cudaEvent_t ev_attn = nullptr, ev_post = nullptr;
+};
 
 struct mg_engine {
     int device = 0;
@@ -118,6 +132,13 @@ struct mg_engine {
     float kc_ms[KC_COUNT] = {0};
     long long *d_timeline = nullptr;   // test hook (mg_test_timeline)
     int *d_attn_ctr = nullptr;         // work counter of the persistent attention kernel (self-resetting)
+    Lane lanes[2];                     // stream lanes (see Lane); lane workspaces are allocated on first use
+    bool lanes_ready = false;
+    int n_lanes = 1;                   // MAPF_GPT_B200_LANES (default: 2 for the C = 160 fused path, else 1)
+    int lane_attn_grid = 0;            // attention CTAs per launch in lane mode (MAPF_GPT_B200_LANE_ATTN_GRID, default n_sms)
+    int **attn_ctr_slot = nullptr;     // which counter launch_attn_persistent uses (a lane's or d_attn_ctr)
+    int attn_grid_cap = 0;             // > 0: grid of the persistent attention kernel (lane mode)
+    cudaEvent_t ev_fork = nullptr;
     CUtensorMap map_c2g{}, map_loc{};  // TMA descriptors of the FOV-window fields (observe_tma_kernel)
     std::vector<std::vector<uint8_t>> map_grids;   // large maps: host copies of the distinct grids (precompute tables per map)
     std::vector<uint16_t *> map_pre;               // device K x K tables
@@ -467,18 +488,20 @@ static int launch_attn_persistent(mg_engine *e, const AttnArgs &a, int n_seq, cu
     AttnArgs aa = a;
     int *tmp_ctr = nullptr;
     if (e) {
-        if (!e->d_attn_ctr) {
-            CU(dalloc(&e->d_attn_ctr, 2));
-            CU(cudaMemsetAsync(e->d_attn_ctr, 0, 8, st));
+        int **slot = e->attn_ctr_slot ? e->attn_ctr_slot : &e->d_attn_ctr;
+        if (!*slot) {
+            CU(dalloc(slot, 2));
+            CU(cudaMemsetAsync(*slot, 0, 8, st));
         }
-        aa.work_counter = e->d_attn_ctr;
+        aa.work_counter = *slot;
     } else {   // test hook without an engine: a counter of its own, freed after the (synchronous) call
         CU(dalloc(&tmp_ctr, 2));
         CU(cudaMemsetAsync(tmp_ctr, 0, 8, st));
         aa.work_counter = tmp_ctr;
     }
     if (e) prof_begin(e, KC_ATTN);
-    attn_persistent_kernel<FAST><<<std::min(n_items, 2 * n_sms), 320, smem, st>>>(aa, n_items);
+    const int grid = e && e->attn_grid_cap > 0 ? e->attn_grid_cap : 2 * n_sms;
+    attn_persistent_kernel<FAST><<<std::min(n_items, grid), 320, smem, st>>>(aa, n_items);
     if (e) prof_end(e);
     CU(cudaGetLastError());
     if (tmp_ctr) {
@@ -515,12 +538,12 @@ static int launch_attn(mg_engine *e, const AttnArgs &a, int hs, int n_seq, cudaS
 }
 
 // ------------------------------------------------------------------------------------------- forward
-static int ensure_workspace(mg_engine *e, int want_seqs)
+static int ensure_workspace(mg_engine *e, Workspace &w, int want_seqs)
 {
-    Workspace &w = e->ws;
     const int C = e->model.cfg.n_embd;
     // sequences per forward chunk (workspace = 22 * chunk * 256 * C bytes); MAPF_GPT_B200_CHUNK_SEQS overrides (multiple of 128)
-    static const int chunk_max = getenv("MAPF_GPT_B200_CHUNK_SEQS") ? std::max(128, atoi(getenv("MAPF_GPT_B200_CHUNK_SEQS")) / 128 * 128) : 8192;
+    // (read when the workspace is first sized: an engine keeps its chunk size)
+    const int chunk_max = getenv("MAPF_GPT_B200_CHUNK_SEQS") ? std::max(128, atoi(getenv("MAPF_GPT_B200_CHUNK_SEQS")) / 128 * 128) : 8192;
     int chunk = std::min(want_seqs, chunk_max);
     if (chunk <= w.chunk_seqs) return MG_OK;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
@@ -616,6 +639,29 @@ static void launch_head_loss(mg_engine *e, const float *X, int compact, const Ev
                                                                              ev.pred + s0, C, ns);
 }
 
+// fork: both lanes start behind everything queued on the engine's stream (the tokens of this timestep)
+static int lanes_begin(mg_engine *e, int chunk_seqs)
+{
+    if (!e->lanes_ready) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        for (Lane &ln : e->lanes) {
+            CU(cudaStreamCreateWithPriority(&ln.lo, cudaStreamNonBlocking, least));
+            CU(cudaStreamCreateWithPriority(&ln.hi, cudaStreamNonBlocking, greatest));
+            CU(cudaEventCreateWithFlags(&ln.ev_attn, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ln.ev_post, cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        e->lanes_ready = true;
+    }
+    cudaStream_t main = e->stream;
+    const int rc = ensure_workspace(e, e->lanes[1].ws, chunk_seqs);   // (its memsets are queued on the engine's stream, before the fork)
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev_fork, main));
+    for (Lane &ln : e->lanes) CU(cudaStreamWaitEvent(ln.lo, e->ev_fork, 0));
+    return MG_OK;
+}
+
 static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float *logits, const EvalOut *ev = nullptr)
 {
     Model &m = e->model;
@@ -624,13 +670,31 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         if (ev) return fail(MG_ERR_STATE, "validation loss is not available in the fp32 verification mode");
         return forward_precise(e, tokens, n_seq, logits);
     }
-    int rc = ensure_workspace(e, n_seq);
+    int rc = ensure_workspace(e, e->ws, n_seq);
     if (rc) return rc;
-    Workspace &w = e->ws;
     const int C = m.cfg.n_embd, H = m.cfg.n_head, hs = m.hs;
-    for (int s0 = 0; s0 < n_seq; s0 += w.chunk_seqs) {
-        const int ns = std::min(w.chunk_seqs, n_seq - s0);
+    // Stream lanes (struct Lane): chunks alternate between two workspaces / stream pairs; per-kernel event timing (profiling),
+    // the validation outputs and the max-subtracting fallback keep the single-stream order.
+    const int chunk_seqs = e->ws.chunk_seqs;
+    const bool lanes = m.fused && hs == 32 && e->n_lanes == 2 && !e->profiling && !ev && n_seq > chunk_seqs &&
+                       getenv("MAPF_GPT_B200_ATTN_CLASSIC") == nullptr;
+    struct LaneScope {   // launches below go to e->stream: point it at the lane's streams and restore on every exit path
+        mg_engine *e; cudaStream_t main;
+        ~LaneScope() { e->stream = main; e->attn_ctr_slot = nullptr; e->attn_grid_cap = 0; }
+    } scope{e, e->stream};
+    if (lanes) {
+        if ((rc = lanes_begin(e, chunk_seqs))) return rc;
+    }
+    for (int s0 = 0, ci = 0; s0 < n_seq; s0 += chunk_seqs, ci++) {
+        const int ns = std::min(chunk_seqs, n_seq - s0);
         const int M = ns * 256, MT = M / 128;
+        Lane *ln = lanes ? &e->lanes[ci & 1] : nullptr;
+        Workspace &w = (ln && (ci & 1)) ? ln->ws : e->ws;   // lane 0 works in the engine's own workspace
+        if (ln) {
+            e->stream = ln->lo;
+            e->attn_ctr_slot = &ln->ctr;
+            e->attn_grid_cap = e->lane_attn_grid > 0 ? e->lane_attn_grid : e->n_sms;
+        }
         if (m.fused) {
             // with >= 2 blocks the first post_attn takes its residual tile from the table itself: the lookup writes q/k/v only
             static const bool x_via_hbm = getenv("MAPF_GPT_B200_BLOCK0_X_VIA_HBM") != nullptr;
@@ -684,7 +748,20 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 static const int stamp_item = getenv("MAPF_GPT_B200_STAMP_ITEM") ? atoi(getenv("MAPF_GPT_B200_STAMP_ITEM")) : 40;
                 at.dbg_variant = stamp_item;   // which item of a persistent attention CTA tools/timeline.py stamps
                 if (l == 0 && gather0) { at.tokens0 = tokens + (size_t)s0 * 256; at.tab0 = m.tab0; at.tab_nrec = C / 4 + 3 * C / 8; at.tab_qkv0 = C / 4; }
-                if ((rc = launch_attn(e, at, hs, ns, e->stream, !e->safe_softmax))) return rc;
+                if (ln) {   // attention on the lane's high-priority stream, behind everything the low-priority one has queued
+                    CU(cudaEventRecord(ln->ev_post, ln->lo));
+                    CU(cudaStreamWaitEvent(ln->hi, ln->ev_post, 0));
+                    e->stream = ln->hi;
+                }
+                rc = launch_attn(e, at, hs, ns, e->stream, !e->safe_softmax);
+                if (ln) {
+                    e->stream = ln->lo;
+                    if (!rc) {
+                        CU(cudaEventRecord(ln->ev_attn, ln->hi));
+                        CU(cudaStreamWaitEvent(ln->lo, ln->ev_attn, 0));
+                    }
+                }
+                if (rc) return rc;
                 PostAttnArgs pa{};
                 pa.att = w.ATT; pa.x = w.X; pa.wstream = L.wstream; pa.wstream_pair = L.wstream_pair; pa.ln2_gain = L.ln2;
                 pa.next_gain = last ? nullptr : m.layers[l + 1].ln1;
@@ -773,6 +850,12 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         head_kernel<<<(ns + 3) / 4, 128, 0, e->stream>>>(w.X, m.lnf, m.wte, logits + (size_t)s0 * 8, C, ns);
         prof_end(e);
         if (ev) launch_head_loss(e, w.X, 0, *ev, s0, ns);
+    }
+    if (lanes) {   // join: the engine's stream continues after both lanes
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventRecord(e->lanes[i].ev_post, e->lanes[i].lo));
+            CU(cudaStreamWaitEvent(scope.main, e->lanes[i].ev_post, 0));
+        }
     }
     CU(cudaGetLastError());
     return MG_OK;
@@ -1173,9 +1256,19 @@ void mg_engine_destroy(mg_engine *e)
     cudaFree(m.wte); cudaFree(m.wpe); cudaFree(m.lnf); cudaFree(m.wpe_ti); cudaFree(m.tab0);
     for (auto &L : m.layers) { cudaFree(L.ln1); cudaFree(L.ln2); cudaFree(L.wqkv); cudaFree(L.wproj); cudaFree(L.wfc); cudaFree(L.wproj2); cudaFree(L.wstream); cudaFree(L.wstream_pair);
                                 cudaFree(L.wqkv_p); cudaFree(L.wproj_p); cudaFree(L.wfc_p); cudaFree(L.wproj2_p); cudaFree(L.cs_qkv); cudaFree(L.cs_fc); }
-    Workspace &w = e->ws;
-    cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
-    cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
+    for (Workspace *wp : {&e->ws, &e->lanes[0].ws, &e->lanes[1].ws}) {
+        Workspace &w = *wp;
+        cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
+        cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
+    }
+    for (Lane &ln : e->lanes) {
+        cudaFree(ln.ctr);
+        if (ln.ev_attn) cudaEventDestroy(ln.ev_attn);
+        if (ln.ev_post) cudaEventDestroy(ln.ev_post);
+        if (ln.lo) cudaStreamDestroy(ln.lo);
+        if (ln.hi) cudaStreamDestroy(ln.hi);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     for (auto &p : e->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
@@ -1234,6 +1327,12 @@ int mg_engine_load_model(mg_engine *e, const mg_model_config *cfg, const float *
     m.layers.resize(cfg->n_layer);
     const char *force_generic = getenv("MAPF_GPT_B200_GENERIC");
     m.fused = (C == 160 || C == 256) && !(force_generic && force_generic[0] == '1');
+    {   // stream lanes (struct Lane): only where an attention CTA and a post_attn CTA fit one SM together (C = 160)
+        const char *ln = getenv("MAPF_GPT_B200_LANES");
+        e->n_lanes = ln ? (atoi(ln) == 2 ? 2 : 1) : MG_LANES_DEFAULT(C);
+        const char *lg = getenv("MAPF_GPT_B200_LANE_ATTN_GRID");
+        e->lane_attn_grid = lg ? atoi(lg) : 0;
+    }
     {
         const char *np = getenv("MAPF_GPT_B200_NO_PRUNE");
         e->prune_last = !(np && np[0] == '1');
@@ -1734,6 +1833,7 @@ int mg_engine_last_timing(mg_engine *e, float *total_ms, float *phases_ms3)
 
 long long mg_engine_launch_count(const mg_engine *e) { return e ? e->launches : 0; }
 
+int mg_engine_num_lanes(const mg_engine *e) { return e ? e->n_lanes : 0; }
 int mg_engine_kernel_times(mg_engine *e, float *ms_out, int n)
 {   // [2*k] = total ms, [2*k+1] = launches, k in KernelClass order
     if (!e || !ms_out) return fail(MG_ERR_ARG, "null argument");

@@ -195,6 +195,9 @@ struct PostAttnCfg {
 // Measured (profiles/r02_post_attn_persistent.md): PERSIST wins where one CTA fits per SM (C = 256: 3.89 -> 3.65 ms per launch)
 // and loses where two do (C = 160: 1.92 -> 1.98 ms; two co-resident CTAs started by the hardware at different times already
 // hide each other's launch gaps, while resident CTAs run in lockstep), so the launcher uses it for C = 256 only.
+#ifndef MG_GELU_MIX_BITS
+#define MG_GELU_MIX_BITS 0
+#endif
 template <int C, int NT, int UU = 0, int CL = 1, bool PERSIST = false>
 __global__ void __launch_bounds__(PostAttnCfg<C, NT, UU, CL>::THREADS, PostAttnCfg<C, NT, UU, CL>::CTAS_PER_SM)
 post_attn_kernel(const PostAttnArgs a)
@@ -678,10 +681,15 @@ post_attn_kernel(const PostAttnArgs a)
                 uint4 o[NV];
 #pragma unroll
                 for (int g = 0; g < NV; g++) {
-                    o[g].x = pack_bf16x2_p(gelu2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1])));
-                    o[g].y = pack_bf16x2_p(gelu2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3])));
-                    o[g].z = pack_bf16x2_p(gelu2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5])));
-                    o[g].w = pack_bf16x2_p(gelu2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7])));
+                    // MG_GELU_MIX_BITS: which of every 8 consecutive pairs take the FMA-only form instead of the MUFU.TANH one
+                    auto act = [&](int k) {
+                        const float x0 = __uint_as_float(v[g][2 * k]), x1 = __uint_as_float(v[g][2 * k + 1]);
+                        return pack_bf16x2_p(((MG_GELU_MIX_BITS >> ((4 * g + k) & 7)) & 1) ? gelu2_fma(x0, x1) : gelu2(x0, x1));
+                    };
+                    o[g].x = act(0);
+                    o[g].y = act(1);
+                    o[g].z = act(2);
+                    o[g].w = act(3);
                 }
                 if (sub == NSUB - 1) MG_WLAP(5);  // GELU
                 if (sub == 0 && j >= 1) {

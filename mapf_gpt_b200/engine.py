@@ -223,6 +223,10 @@ class RolloutEngine:
     def launch_count(self) -> int:
         return int(self._L.mg_engine_launch_count(self._h))
 
+    def num_lanes(self) -> int:
+        """Stream lanes of the forward (2 = attention and post-attention kernels of alternate chunks overlap)."""
+        return int(self._L.mg_engine_num_lanes(self._h))
+
     def kernel_times(self) -> dict:
         buf = (C.c_float * (2 * len(KERNEL_CLASSES)))()
         self._L.mg_engine_kernel_times(self._h, buf, len(buf))

@@ -109,6 +109,32 @@ def test_max_free_softmax_falls_back_when_scores_leave_its_range(built, monkeypa
     assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
 
 
+@pytest.mark.parametrize("rows", [640, 700, 256])
+def test_stream_lanes_are_bit_identical_to_the_single_stream_order(built, monkeypatch, rows):
+    """Stream lanes (engine.cu: struct Lane): the chunks of a forward alternate between two workspaces / stream pairs so that
+    attention of one chunk overlaps the post-attention kernels of the other.  Scheduling only: logits bit-identical to the
+    single-stream order, for an even and an odd number of chunks, a ragged last chunk, and repeated calls (workspace reuse)."""
+    from mapf_gpt_b200 import engine as E
+    cfg, sd = sharp_model("2M")
+    toks = np.random.default_rng(rows).integers(0, 67, size=(rows, 256)).astype(np.int8)
+    monkeypatch.setenv("MAPF_GPT_B200_CHUNK_SEQS", "128")
+    outs = []
+    for lanes in ("1", "2"):
+        monkeypatch.setenv("MAPF_GPT_B200_LANES", lanes)
+        eng = E.RolloutEngine(1, 4, 16, 16)
+        eng.load_model(sd, cfg)
+        assert eng.num_lanes() == int(lanes)
+        a = eng.forward_tokens(toks)
+        b = eng.forward_tokens(toks[::-1].copy())[::-1]
+        c = eng.forward_tokens(toks)
+        assert np.array_equal(a, c)
+        outs.append((a, b))
+        eng.close()
+    assert np.isfinite(outs[0][0]).all()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert float(np.abs(outs[1][0] - oracle_logits(sd, cfg, toks.astype(np.int64))).max()) < LOGIT_TOL
+
+
 # ------------------------------------------------------------------------------------------------ full-size parity
 @pytest.mark.parametrize("name,n,envs,model", [("wfi_warehouse", 192, 512, "6M"), ("Berlin_1_256_05", 256, 32, "85M"),
                                                ("validation-mazes-seed-000", 256, 256, "2M")])
