@@ -543,7 +543,7 @@ static int ensure_workspace(mg_engine *e, Workspace &w, int want_seqs)
     const int C = e->model.cfg.n_embd;
     // sequences per forward chunk (workspace = 22 * chunk * 256 * C bytes); MAPF_GPT_B200_CHUNK_SEQS overrides (multiple of 128)
     // (read when the workspace is first sized: an engine keeps its chunk size)
-    const int chunk_max = getenv("MAPF_GPT_B200_CHUNK_SEQS") ? std::max(128, atoi(getenv("MAPF_GPT_B200_CHUNK_SEQS")) / 128 * 128) : 8192;
+    const int chunk_max = getenv("MAPF_GPT_B200_CHUNK_SEQS") ? std::max(128, atoi(getenv("MAPF_GPT_B200_CHUNK_SEQS")) / 4 * 4) : 8192;
     int chunk = std::min(want_seqs, chunk_max);
     if (chunk <= w.chunk_seqs) return MG_OK;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
