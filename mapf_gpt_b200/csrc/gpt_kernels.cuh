@@ -1244,6 +1244,8 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
                 if constexpr (FAST) {
                     // max-free: S is already in the log2 domain (scale folded into Wq), P = 2^S; 64 columns per TMEM round trip
                     f32x2 unused = pk2(0.f, 0.f);
+                    // (32-column batches with the TMEM read of batch b+1 issued before the exponentials of batch b -- same register
+                    // budget -- were measured SLOWER: 0.840 -> 0.861 ms per launch, profiles/r02_experiments.md)
 #pragma unroll 1
                     for (int cb = 0; cb < 2; cb++) {
                         uint32_t v[64], w[32];
