@@ -135,6 +135,31 @@ def test_stream_lanes_are_bit_identical_to_the_single_stream_order(built, monkey
     assert float(np.abs(outs[1][0] - oracle_logits(sd, cfg, toks.astype(np.int64))).max()) < LOGIT_TOL
 
 
+def test_stream_lanes_rollout_equals_the_single_stream_rollout(built, monkeypatch):
+    """The same through the whole path (device-resident rollout and the host-buffer verb): with two lanes the sampled actions,
+    positions and episode metrics of a multi-chunk rollout equal the single-stream ones."""
+    from mapf_gpt_b200 import engine as E
+    cfg, sd = sharp_model("2M")
+    grid, st, gl = instances("validation-mazes-seed-000", 48, 8)          # 384 sequences = 3 chunks of 128
+    monkeypatch.setenv("MAPF_GPT_B200_CHUNK_SEQS", "128")
+    outs = []
+    for lanes in ("1", "2"):
+        monkeypatch.setenv("MAPF_GPT_B200_LANES", lanes)
+        eng = E.RolloutEngine(8, 48, *grid.shape)
+        eng.load_model(sd, cfg)
+        eng.set_seed(7)
+        eng.reset(0, grid, st, gl)
+        eng.rollout(6, E.MODE_PHILOX)
+        pos = eng.positions()
+        acts = eng.act_host(pos, gl, E.MODE_PHILOX)
+        pos2 = eng.env_step(None)
+        outs.append((pos.copy(), acts.copy(), pos2.copy(), eng.metrics().copy()))
+        eng.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    assert (outs[0][0] != st).any()                                       # agents did move
+
+
 # ------------------------------------------------------------------------------------------------ full-size parity
 @pytest.mark.parametrize("name,n,envs,model", [("wfi_warehouse", 192, 512, "6M"), ("Berlin_1_256_05", 256, 32, "85M"),
                                                ("validation-mazes-seed-000", 256, 256, "2M")])
