@@ -243,6 +243,15 @@ post_attn_kernel(const PostAttnArgs a)
     uint32_t mg_group = blockIdx.x;               // group being processed (timeline stamps)
 
     const int n_stages = K::TOTAL_STAGES + (fuse_qkv ? K::QKV_STAGES : 0);
+    // clock probe (tools/clock_probe.py): SM cycles and wall nanoseconds over one mid-grid CTA -> the SM clock this kernel really
+    // runs at inside a long, power-capped step
+    const bool clk_probe = a.timeline != nullptr && threadIdx.x == 0 && blockIdx.x == ((gridDim.x / 2) & ~1u);
+    if (clk_probe) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.timeline[2112] = clock64();
+        a.timeline[2113] = gt;
+    }
     if (a.stagger_ns > 0) {
         // Persistent launch: identical CTAs started together stay in lockstep, so every HBM phase (residual / att loads, x' and
         // q/k/v stores) would be a device-wide burst with the memory system idle in between (measured: 8.5k cycles per tile
@@ -823,6 +832,12 @@ post_attn_kernel(const PostAttnArgs a)
         }   // tile groups
     }
     if (threadIdx.x == 0) MG_STAMP(91);
+    if (clk_probe) {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.timeline[2114] = clock64();
+        a.timeline[2115] = gt;
+    }
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();         // no CTA leaves (or frees TMEM) while the pair's UMMAs / commits may still target it

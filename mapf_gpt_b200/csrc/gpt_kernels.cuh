@@ -1120,6 +1120,10 @@ __global__ void __launch_bounds__(320, 2) attn_persistent_kernel(const AttnArgs 
         long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         a.timeline[512 + blockIdx.x] = gt;
+        if (blockIdx.x == 100) {   // clock probe (tools/clock_probe.py): SM cycles next to the wall time of this CTA
+            a.timeline[2120] = clock64();
+            a.timeline[2121] = gt;
+        }
     }
     const size_t blk = (size_t)(HS / 8) * 256 * 8;   // elements per (seq, which, head)
 
@@ -1349,6 +1353,10 @@ done:
         long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         a.timeline[1536 + blockIdx.x] = gt;
+        if (blockIdx.x == 100) {
+            a.timeline[2122] = clock64();
+            a.timeline[2123] = gt;
+        }
     }
     if (warp == 9) tmem_dealloc<256>(tmem);
 }
