@@ -301,6 +301,9 @@ static int upload_post_attn_stream(const float *Wproj, const float *Wfc, const f
     return MG_OK;
 }
 
+#ifndef MG_POST_PF_DEFAULT
+#define MG_POST_PF_DEFAULT(slots) ((slots) / 4)
+#endif
 #ifndef MG_POST_CL_DEFAULT
 #define MG_POST_CL_DEFAULT 2
 #endif
@@ -337,6 +340,12 @@ static int launch_post_attn_c(mg_engine *e, PostAttnArgs a, int MT, int kc)
             cfg.gridDim = dim3(cap);
             a.stagger_ns = stagger_override;   // spreading the cluster start times over a tile period measured neutral: off by default
         }
+    }
+    if (!PERSIST) {
+        // successor prefetch distance (MAPF_GPT_B200_POST_PF overrides; 0 = off): a quarter of the device's CTA slots measured best
+        // (32-96 of 296: post_attn<160> 1.80 -> 1.75 ms per launch; 148: 1.74-1.79; the full 296 and beyond: 1.82-1.84, slower than none)
+        static const int pf_override = getenv("MAPF_GPT_B200_POST_PF") ? atoi(getenv("MAPF_GPT_B200_POST_PF")) : -1;
+        a.pf_dist = pf_override >= 0 ? pf_override : MG_POST_PF_DEFAULT(K::CTAS_PER_SM * e->n_sms);
     }
     prof_begin(e, kc);
     CU((cudaLaunchKernelEx(&cfg, post_attn_kernel<C, NT, UU, CL, PERSIST>, a)));
@@ -770,6 +779,9 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 pa.n_head = H; pa.hs = hs;
                 pa.timeline = e->d_timeline;
                 if (l == 0 && x_from_tab) { pa.tokens0 = tokens + (size_t)s0 * 256; pa.tab0 = m.tab0; pa.tab_nrec = C / 4 + 3 * C / 8; }
+                // the next block is the pruned last one: it reads the residual and q of token 255 only (last_attn_kernel)
+                static const bool full_tail = getenv("MAPF_GPT_B200_FULL_TAIL_STORES") != nullptr;
+                pa.tail_rows_only = (e->prune_last && l + 2 == m.cfg.n_layer && m.fuse_qkv && !full_tail) ? 1 : 0;
                 if ((rc = launch_post_attn(e, C, pa, MT, false))) return rc;
             }
             if (e->prune_last) continue;

@@ -45,6 +45,13 @@ struct PostAttnArgs {
     // CTAs and keeps barriers, TMEM and the weight ring alive across tiles.
     int n_groups;
     int stagger_ns;                // persistent launch: start offsets of the clusters are spread over this many ns (0 = none)
+    // one-group-per-CTA launch: at its start a CTA asks L2 for the att / residual tiles of the CTA that will take over its slot
+    // (group blockIdx.x + pf_dist, pf_dist = resident CTAs), so that CTA's first loads hit L2 instead of queueing behind the
+    // stores of 295 other CTAs in the DRAM controllers.  0 = off.
+    int pf_dist;
+    // the block after this one is the pruned last block (only token 255 of each sequence goes on): of the updated residual and of
+    // the next block's q rows only those of token 255 are stored (k and v are needed for every token) -- 6C of 16C bytes per token
+    int tail_rows_only;
 };
 // steady-state tile groups (not the first wave, whose loads all hit DRAM at once), keyed by the group index `mg_group` in scope;
 // single-tile launches have fewer groups and stamp nothing
@@ -286,6 +293,13 @@ post_attn_kernel(const PostAttnArgs a)
         for (int i = 0; i < S && i < n_stages; i++) {
             mbar_expect_tx(&full[i], K::SLOT_BYTES);
             bulk_g2s(ring + i * K::SLOT_BYTES, src + (size_t)i * K::STAGE_BYTES + crank * K::SLOT_BYTES, K::SLOT_BYTES, &full[i]);
+        }
+        if constexpr (!PERSIST) {
+            const int nb = (int)blockIdx.x + a.pf_dist;
+            if (a.pf_dist > 0 && nb < a.n_groups) {
+                bulk_prefetch_l2(a.att + (size_t)nb * NT * C * 128, NT * C * 128 * 2);
+                if (a.tab0 == nullptr) bulk_prefetch_l2(a.x + (size_t)nb * NT * C * 128, NT * C * 128 * 4);
+            }
         }
     }
     constexpr int HALF = C / NH;                          // residual columns handled by one worker thread
@@ -582,6 +596,7 @@ post_attn_kernel(const PostAttnArgs a)
         const uint32_t ph = it & 1;                       // parity of the barriers that complete once per tile
         const int mt = g * NT + t;
         float4 *Xg = reinterpret_cast<float4 *>(a.x) + (size_t)mt * (C / 4) * 128 + r;
+        const bool keep_row = !a.tail_rows_only || ((mt & 1) && r == 127);   // token 255 = row 127 of the sequence's second tile
 
         // ---- x -> TMEM accumulator (overlaps the att tile load); c_proj then accumulates onto it.
         // All loads are issued before the first TMEM store so the thread pays ONE memory round trip.
@@ -728,6 +743,7 @@ post_attn_kernel(const PostAttnArgs a)
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < N / 4; j++) {
+                    if (keep_row)
                     __stcs(&Xg[(size_t)((h * HALF + C0) / 4 + j) * 128], make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
                                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     const f32x2 e0 = pk2u(v[4 * j + 0], v[4 * j + 1]), e1 = pk2u(v[4 * j + 2], v[4 * j + 3]);
@@ -817,6 +833,7 @@ post_attn_kernel(const PostAttnArgs a)
                     o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
                     o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
                     o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                    if (hh >= 2 || keep_row)   // hh 0, 1 = the q columns
                     __stcs(&Oseq[qkv_off[(hh * HC + h * (HC / NH)) / 8 + j]], o);   // streaming: 3.4 GB per launch pass through L2 once
                 }
                 MG_WLAP(12);  // q/k/v half-tile -> HBM
