@@ -782,6 +782,11 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 // the next block is the pruned last one: it reads the residual and q of token 255 only (last_attn_kernel)
                 static const bool full_tail = getenv("MAPF_GPT_B200_FULL_TAIL_STORES") != nullptr;
                 pa.tail_rows_only = (e->prune_last && l + 2 == m.cfg.n_layer && m.fuse_qkv && !full_tail) ? 1 : 0;
+                // 24-bit residual stream between consecutive post_attn launches (pack24x16); the rows last_attn_kernel / head_kernel
+                // read stay fp32.  MAPF_GPT_B200_X24=0 keeps fp32 everywhere.
+                static const bool x24 = !(getenv("MAPF_GPT_B200_X24") && getenv("MAPF_GPT_B200_X24")[0] == '0');
+                pa.x_in_24 = (x24 && l > 0) ? 1 : 0;
+                pa.x_out_24 = (x24 && !last && !pa.tail_rows_only && !(e->prune_last && l + 2 == m.cfg.n_layer)) ? 1 : 0;
                 if ((rc = launch_post_attn(e, C, pa, MT, false))) return rc;
             }
             if (e->prune_last) continue;

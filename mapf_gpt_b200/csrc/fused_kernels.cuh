@@ -52,6 +52,7 @@ struct PostAttnArgs {
     // the block after this one is the pruned last block (only token 255 of each sequence goes on): of the updated residual and of
     // the next block's q rows only those of token 255 are stored (k and v are needed for every token) -- 6C of 16C bytes per token
     int tail_rows_only;
+    int x_in_24, x_out_24;         // a.x is read / written in the 24-bit tile layout (pack24x16) instead of fp32
 };
 // steady-state tile groups (not the first wave, whose loads all hit DRAM at once), keyed by the group index `mg_group` in scope;
 // single-tile launches have fewer groups and stamp nothing
@@ -122,6 +123,44 @@ template <int V> struct IntC { static constexpr int value = V; };
             F(IntC<96>{}, IntC<32>{});                                           \
         }                                                                        \
     } while (0)
+// 24-bit residual stream between post_attn launches: the updated residual travels through HBM as the TOP 24 bits of each fp32
+// value (sign, exponent, 15 mantissa bits, rounded to nearest: relative error 2^-17, two orders of magnitude below the bf16
+// operand rounding applied to it next) -- 6C instead of 8C bytes per token and block for the round trip.  Tile layout
+// [C/16][3][128 rows][16 B]: 16 consecutive columns of a row = 48 bytes = three 16-byte pieces, each piece row-contiguous.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ void pack24x16(const uint32_t *v, uint4 (&o)[3])
+{
+    uint32_t w[12];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t f0 = v[4 * q] + 0x80u, f1 = v[4 * q + 1] + 0x80u, f2 = v[4 * q + 2] + 0x80u, f3 = v[4 * q + 3] + 0x80u;
+        w[3 * q] = prmt(f0, f1, 0x5321u);       // f0.b1 f0.b2 f0.b3 f1.b1
+        w[3 * q + 1] = prmt(f1, f2, 0x6532u);   // f1.b2 f1.b3 f2.b1 f2.b2
+        w[3 * q + 2] = prmt(f2, f3, 0x7653u);   // f2.b3 f3.b1 f3.b2 f3.b3
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+// (the low byte of each result is a neighbour's byte: noise at 2^-24 relative, deterministic)
+__device__ __forceinline__ void unpack24x16(const float4 &i0, const float4 &i1, const float4 &i2, uint32_t *v)
+{
+    const uint32_t w[12] = {__float_as_uint(i0.x), __float_as_uint(i0.y), __float_as_uint(i0.z), __float_as_uint(i0.w),
+                            __float_as_uint(i1.x), __float_as_uint(i1.y), __float_as_uint(i1.z), __float_as_uint(i1.w),
+                            __float_as_uint(i2.x), __float_as_uint(i2.y), __float_as_uint(i2.z), __float_as_uint(i2.w)};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        v[4 * q] = prmt(a, a, 0x2103u);
+        v[4 * q + 1] = prmt(a, b, 0x5432u);
+        v[4 * q + 2] = prmt(b, c, 0x4321u);
+        v[4 * q + 3] = c;
+    }
+}
 // sum of squared deviations of 16 values, packed
 __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean, f32x2 acc)
 {
@@ -298,7 +337,7 @@ post_attn_kernel(const PostAttnArgs a)
             const int nb = (int)blockIdx.x + a.pf_dist;
             if (a.pf_dist > 0 && nb < a.n_groups) {
                 bulk_prefetch_l2(a.att + (size_t)nb * NT * C * 128, NT * C * 128 * 2);
-                if (a.tab0 == nullptr) bulk_prefetch_l2(a.x + (size_t)nb * NT * C * 128, NT * C * 128 * 4);
+                if (a.tab0 == nullptr) bulk_prefetch_l2(a.x + (size_t)nb * NT * C * 128, NT * C * 128 * (a.x_in_24 ? 3 : 4));
             }
         }
     }
@@ -311,6 +350,10 @@ post_attn_kernel(const PostAttnArgs a)
             const float4 *src = reinterpret_cast<const float4 *>(a.tab0 + ((size_t)tok * 256 + ((mtl & 1) << 7) + row) * a.tab_nrec) + hh * (HALF / 4);
 #pragma unroll
             for (int j = 0; j < HALF / 4; j++) xv[j] = __ldg(src + j);
+        } else if (a.x_in_24) {   // 3 pieces per 16 columns; the raw pieces wait in xv[0 .. 3 HALF/16) until the TMEM stores
+            const float4 *Xl = reinterpret_cast<const float4 *>(a.x) + (size_t)mtl * (C / 4) * 128 + row;
+#pragma unroll
+            for (int j = 0; j < 3 * HALF / 16; j++) xv[j] = Xl[(size_t)(hh * (3 * HALF / 16) + j) * 128];
         } else {
             const float4 *Xl = reinterpret_cast<const float4 *>(a.x) + (size_t)mtl * (C / 4) * 128 + row;
 #pragma unroll
@@ -392,7 +435,7 @@ post_attn_kernel(const PostAttnArgs a)
                     }
                 }
                 if (g + gstride < n_groups && a.tab0 == nullptr)   // the next tile's residual: on its way into L2 during this tile
-                    bulk_prefetch_l2(a.x + (size_t)(g + gstride) * NT * C * 128, NT * C * 128 * 4);
+                    bulk_prefetch_l2(a.x + (size_t)(g + gstride) * NT * C * 128, NT * C * 128 * (a.x_in_24 ? 3 : 4));
                 for (int i = it == 0 ? gi : 0; i < n_stages; i++, gi++) {
                     const int s = gi % S;
                     mbar_wait(&empty[s], ((gi / S) & 1) ^ 1);
@@ -602,6 +645,14 @@ post_attn_kernel(const PostAttnArgs a)
         // All loads are issued before the first TMEM store so the thread pays ONE memory round trip.
         {
             if constexpr (PERSIST) load_x(mt);            // all loads in flight, then the stores (L2 prefetch sent a tile ago)
+            if (a.x_in_24 && a.tab0 == nullptr) {
+#pragma unroll
+                for (int i = 0; i < HALF / 16; i++) {
+                    uint32_t v[16];
+                    unpack24x16(xv[3 * i], xv[3 * i + 1], xv[3 * i + 2], v);
+                    tmem_st16(trow + h * HALF + 16 * i, v);
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < HALF / 16; i++) {
                 uint32_t v[16];
@@ -611,6 +662,7 @@ post_attn_kernel(const PostAttnArgs a)
                     v[4 * j + 2] = __float_as_uint(xv[4 * i + j].z); v[4 * j + 3] = __float_as_uint(xv[4 * i + j].w);
                 }
                 tmem_st16(trow + h * HALF + 16 * i, v);
+            }
             }
         }
         tmem_wait_st();
@@ -741,9 +793,19 @@ post_attn_kernel(const PostAttnArgs a)
                 uint32_t v[N];
                 tmem_ld_n<N>(trow + h * HALF + C0, v);
                 tmem_wait_ld();
+                if (a.x_out_24) {
+#pragma unroll
+                    for (int gq = 0; gq < N / 16; gq++) {
+                        uint4 o[3];
+                        pack24x16(&v[16 * gq], o);
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            __stcs(reinterpret_cast<uint4 *>(&Xg[(size_t)(((h * HALF + C0) / 16 + gq) * 3 + k) * 128]), o[k]);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < N / 4; j++) {
-                    if (keep_row)
+                    if (keep_row && !a.x_out_24)
                     __stcs(&Xg[(size_t)((h * HALF + C0) / 4 + j) * 128], make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
                                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     const f32x2 e0 = pk2u(v[4 * j + 0], v[4 * j + 1]), e1 = pk2u(v[4 * j + 2], v[4 * j + 3]);

@@ -1,0 +1,25 @@
+#!/bin/bash
+# 24-bit residual stream between post_attn launches (MAPF_GPT_B200_X24=0 = fp32): tests, flip rate, A/B
+cd "$(dirname "$0")/../.."
+O=gpurun_out/r02an; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py tests/test_gpu_rollout.py -m gpu -x -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -5 $O/tests.log
+for m in 2M 6M; do python tools/flip_rate.py $m > $O/flip_$m.txt 2>&1; cut -c1-300 $O/flip_$m.txt | tail -3; MAPF_GPT_B200_X24=0 python tools/flip_rate.py $m > $O/flip_${m}_fp32.txt 2>&1; cut -c1-300 $O/flip_${m}_fp32.txt | tail -3; done
+run() { name=$1; shift
+  env "$@" timeout 300 python bench.py --quick --steps 8 --warmup 3 $ARGS > $O/b_$name.json 2>$O/b_$name.err
+  python - <<PY
+import json
+f="$O/b_$name.json"
+try:
+    d=json.loads(open(f).read().strip().splitlines()[-1])
+    print("$name", round(d['value']), d['roofline']['whole_step_frac'], round(d['ms_per_step'],2), {k:v['avg_ms'] for k,v in d['kernels'].items() if v['share']>0.01}, d['clocks']['sm_mhz'], d['clocks'].get('power_w_max'))
+except Exception as ex: print(f,'ERR',ex, open(f.replace('.json','.err')).read()[-600:])
+PY
+}
+for rep in 1 2; do
+ARGS=""
+run fp32_$rep MAPF_GPT_B200_X24=0
+run x24_$rep X=1
+ARGS="--model 6M --map wfi_warehouse --agents 192 --envs 512 --steps 4"
+run 6M_fp32_$rep MAPF_GPT_B200_X24=0
+run 6M_x24_$rep X=1
+done
