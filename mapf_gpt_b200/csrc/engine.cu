@@ -85,6 +85,7 @@ struct Workspace {
     float *X = nullptr;
     __nv_bfloat16 *XN = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr;
     float *STATS = nullptr;           // LayerNorm folded into the GEMMs: [M/128][C/128][2][128] partial row sums / sums of squares
+    float *X24 = nullptr;             // generic path: the residual in its 24-bit layout between the residual GEMMs (same tile pitch)
     float *Xc = nullptr;              // compact residual rows of token 255 (last-block pruning)
     __nv_bfloat16 *ATTc = nullptr;    // compact attention output of token 255
     uint8_t *tok = nullptr;   // staging for forward_tokens
@@ -446,6 +447,7 @@ static int launch_gemm(mg_engine *e, int BN, const GemmArgs &a, int kc)
     const bool pair_off = getenv("MAPF_GPT_B200_GEMM_PAIR") && getenv("MAPF_GPT_B200_GEMM_PAIR")[0] == '0';   // per launch: tests flip it
     if (a.Wp && !pair_off && BN == 256 && a.N % 256 == 0 && a.K % 64 == 0 && (a.M / 128) % 2 == 0)
         return launch_gemm_pair_persistent<EPI>(e, a, kc);
+    if (a.x_in_24 || a.x_out_24) return fail(MG_ERR_STATE, "gemm: the 24-bit residual layout needs the CTA-pair kernel");
     // (a single-stage K=160 variant <160,160,1> measured SLOWER, 0.68 vs 0.60 ms: no load/UMMA overlap inside the CTA)
     if (BN == 160 && a.N % 160 == 0 && a.K % 32 == 0) return launch_gemm_cfg<160, 32, 4, EPI>(e, a, kc);
     if (BN == 256 && a.N % 256 == 0 && a.K % 64 == 0) return launch_gemm_cfg<256, 64, 2, EPI>(e, a, kc);
@@ -556,9 +558,11 @@ static int ensure_workspace(mg_engine *e, Workspace &w, int want_seqs)
     int chunk = std::min(want_seqs, chunk_max);
     if (chunk <= w.chunk_seqs) return MG_OK;
     cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
-    w.X = w.Xc = w.STATS = nullptr; w.XN = w.QKV = w.ATT = w.HID = w.ATTc = nullptr; w.chunk_seqs = 0;
+    cudaFree(w.X24);
+    w.X = w.Xc = w.STATS = w.X24 = nullptr; w.XN = w.QKV = w.ATT = w.HID = w.ATTc = nullptr; w.chunk_seqs = 0;
     const size_t M = (size_t)chunk * 256;
     if (e->model.ln_fused) CU(dalloc(&w.STATS, M * 2 * (C / 128)));
+    if (e->model.ln_fused) CU(dalloc(&w.X24, M * C));
     CU(dalloc(&w.X, M * C));
     CU(dalloc(&w.XN, M * C));
     CU(dalloc(&w.QKV, M * 3 * C));
@@ -798,6 +802,12 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         }
         const bool lnf = m.ln_fused;    // ln_1 / ln_2 live in the epilogues of the GEMMs around them; w.XN holds the RAW bf16 residual
         bool pruned_tail = false;
+        // 24-bit residual stream between the residual GEMMs of the CTA-pair path (GemmArgs::x_in_24 / x_out_24): everything between
+        // embed_kernel (writes fp32) and the last full-size residual GEMM (writes fp32 for last_attn_kernel / head_kernel)
+        static const bool x24_env = !(getenv("MAPF_GPT_B200_X24") && getenv("MAPF_GPT_B200_X24")[0] == '0');
+        const bool x24 = x24_env && lnf;
+        const bool tail_pruned = e->prune_last && (hs == 32 || hs == 64) && 32 * H <= 512;
+        const int last_full = tail_pruned ? m.cfg.n_layer - 2 : m.cfg.n_layer - 1;   // block whose mlp c_proj is the last full-size one
         prof_begin(e, KC_EMBED);
         embed_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, C, lnf ? w.XN : nullptr, w.STATS);
         prof_end(e);
@@ -847,6 +857,10 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             g = GemmArgs{};
             g.A = w.ATT; g.W = L.wproj; g.Wp = L.wproj_p; g.out = w.X; g.M = M; g.N = C; g.K = C;
             if (lnf) { g.xb_out = w.XN; g.stats_out = w.STATS; }                       // operand + statistics of ln_2
+            if (x24 && g.Wp) {   // block 0 changes the layout: fp32 from w.X -> 24-bit into w.X24; later blocks stay in w.X24
+                g.x_in_24 = l > 0; g.x_out_24 = 1;
+                g.resid_in = l > 0 ? w.X24 : w.X; g.out = w.X24;
+            }
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ))) return rc;
             if (!lnf) {
                 prof_begin(e, KC_LN);
@@ -860,6 +874,10 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             g = GemmArgs{};
             g.A = w.HID; g.W = L.wproj2; g.Wp = L.wproj2_p; g.out = w.X; g.M = M; g.N = C; g.K = 4 * C;
             if (lnf && l + 1 < m.cfg.n_layer) { g.xb_out = w.XN; g.stats_out = w.STATS; }   // ... of the next block's ln_1
+            if (x24 && g.Wp) {   // the last full-size one changes the layout back: 24-bit from w.X24 -> fp32 into w.X
+                g.x_in_24 = 1; g.x_out_24 = l < last_full;
+                g.resid_in = w.X24; g.out = l < last_full ? w.X24 : w.X;
+            }
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ2))) return rc;
         }
         if (pruned_tail) continue;
@@ -1276,7 +1294,7 @@ void mg_engine_destroy(mg_engine *e)
     for (Workspace *wp : {&e->ws, &e->lanes[0].ws, &e->lanes[1].ws}) {
         Workspace &w = *wp;
         cudaFree(w.X); cudaFree(w.XN); cudaFree(w.QKV); cudaFree(w.ATT); cudaFree(w.HID); cudaFree(w.tok); cudaFree(w.logits);
-        cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS);
+        cudaFree(w.Xc); cudaFree(w.ATTc); cudaFree(w.STATS); cudaFree(w.X24);
     }
     for (Lane &ln : e->lanes) {
         cudaFree(ln.ctr);

@@ -123,44 +123,6 @@ template <int V> struct IntC { static constexpr int value = V; };
             F(IntC<96>{}, IntC<32>{});                                           \
         }                                                                        \
     } while (0)
-// 24-bit residual stream between post_attn launches: the updated residual travels through HBM as the TOP 24 bits of each fp32
-// value (sign, exponent, 15 mantissa bits, rounded to nearest: relative error 2^-17, two orders of magnitude below the bf16
-// operand rounding applied to it next) -- 6C instead of 8C bytes per token and block for the round trip.  Tile layout
-// [C/16][3][128 rows][16 B]: 16 consecutive columns of a row = 48 bytes = three 16-byte pieces, each piece row-contiguous.
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
-}
-__device__ __forceinline__ void pack24x16(const uint32_t *v, uint4 (&o)[3])
-{
-    uint32_t w[12];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t f0 = v[4 * q] + 0x80u, f1 = v[4 * q + 1] + 0x80u, f2 = v[4 * q + 2] + 0x80u, f3 = v[4 * q + 3] + 0x80u;
-        w[3 * q] = prmt(f0, f1, 0x5321u);       // f0.b1 f0.b2 f0.b3 f1.b1
-        w[3 * q + 1] = prmt(f1, f2, 0x6532u);   // f1.b2 f1.b3 f2.b1 f2.b2
-        w[3 * q + 2] = prmt(f2, f3, 0x7653u);   // f2.b3 f3.b1 f3.b2 f3.b3
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-}
-// (the low byte of each result is a neighbour's byte: noise at 2^-24 relative, deterministic)
-__device__ __forceinline__ void unpack24x16(const float4 &i0, const float4 &i1, const float4 &i2, uint32_t *v)
-{
-    const uint32_t w[12] = {__float_as_uint(i0.x), __float_as_uint(i0.y), __float_as_uint(i0.z), __float_as_uint(i0.w),
-                            __float_as_uint(i1.x), __float_as_uint(i1.y), __float_as_uint(i1.z), __float_as_uint(i1.w),
-                            __float_as_uint(i2.x), __float_as_uint(i2.y), __float_as_uint(i2.z), __float_as_uint(i2.w)};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
-        v[4 * q] = prmt(a, a, 0x2103u);
-        v[4 * q + 1] = prmt(a, b, 0x5432u);
-        v[4 * q + 2] = prmt(b, c, 0x4321u);
-        v[4 * q + 3] = c;
-    }
-}
 // sum of squared deviations of 16 values, packed
 __device__ __forceinline__ f32x2 sqdev16(const uint32_t (&v)[16], f32x2 negmean, f32x2 acc)
 {

@@ -33,6 +33,12 @@ struct GemmArgs {
     float *stats_out;
     const float *stats_in;
     const float *colsum;
+    // EPI_RESID of the pair GEMM: the residual is read / written as its top 24 bits (pack24x16, tile layout
+    // [N/16][3][128][16 B] inside the fp32 tile's space) instead of fp32
+    int x_in_24, x_out_24;
+    // residual INPUT when it is not `out` itself: a launch that changes the layout (fp32 -> 24-bit or back) must not run in
+    // place -- the two layouts put different columns at the same address, and other CTAs / threads still read theirs
+    const float *resid_in;
 };
 
 // erf-GELU (model.py:80, nn.GELU() = x * Phi(x)) on a PAIR of values with packed fp32x2 math.  Three forms, one compiled in.
@@ -298,29 +304,67 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
     const int nbase = nt * BN + hsel * HALF;
     if constexpr (EPI == EPI_RESID) {
         float4 *X = reinterpret_cast<float4 *>(a.out) + ((size_t)mt * (a.N / 4) + nbase / 4) * 128 + r;
+        float4 *X24 = reinterpret_cast<float4 *>(a.out) + ((size_t)mt * (a.N / 4) + (nbase / 16) * 3) * 128 + r;   // 24-bit layout
+        const float *rin = a.resid_in ? a.resid_in : reinterpret_cast<const float *>(a.out);
+        const float4 *Xi = reinterpret_cast<const float4 *>(rin) + ((size_t)mt * (a.N / 4) + nbase / 4) * 128 + r;
+        const float4 *Xi24 = reinterpret_cast<const float4 *>(rin) + ((size_t)mt * (a.N / 4) + (nbase / 16) * 3) * 128 + r;
+        const bool in24 = a.x_in_24 != 0, out24 = a.x_out_24 != 0;
         float4 xa[8], xb[8];
+        if (in24) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) xa[j] = X[(size_t)j * 128];          // first chunk: on its way while the UMMAs run
+            for (int j = 0; j < 6; j++) xa[j] = Xi24[(size_t)j * 128];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) xa[j] = Xi[(size_t)j * 128];     // first chunk: on its way while the UMMAs run
+        }
         wait_acc();
         const bool ln_out = a.xb_out != nullptr;
         uint4 *XB = reinterpret_cast<uint4 *>(a.xb_out) + ((size_t)mt * (a.N / 8) + nbase / 8) * 128 + r;
         f32x2 s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
         auto chunk = [&](int c0, float4 (&x)[8], float4 (&xn)[8]) {
             if (c0 + 32 < HALF) {
+                if (in24) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) xn[j] = X[(size_t)((c0 + 32) / 4 + j) * 128];
+                    for (int j = 0; j < 6; j++) xn[j] = Xi24[(size_t)((c0 + 32) / 16 * 3 + j) * 128];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) xn[j] = Xi[(size_t)((c0 + 32) / 4 + j) * 128];
+                }
             }
             uint32_t v[32];
             tmem_ld32(trow + c0, v);
             tmem_wait_ld();
             if (c0 + 32 >= HALF) drained();
+            if (in24) {   // 6 pieces -> 32 values
+                uint32_t u[32];
+                unpack24x16(x[0], x[1], x[2], &u[0]);
+                unpack24x16(x[3], x[4], x[5], &u[16]);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    x[j] = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]), __uint_as_float(u[4 * j + 3]));
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 x[j].x += __uint_as_float(v[4 * j + 0]);
                 x[j].y += __uint_as_float(v[4 * j + 1]);
                 x[j].z += __uint_as_float(v[4 * j + 2]);
                 x[j].w += __uint_as_float(v[4 * j + 3]);
-                X[(size_t)(c0 / 4 + j) * 128] = x[j];
+                if (!out24) X[(size_t)(c0 / 4 + j) * 128] = x[j];
+            }
+            if (out24) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    uint32_t u[16];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        u[4 * j] = __float_as_uint(x[4 * g + j].x); u[4 * j + 1] = __float_as_uint(x[4 * g + j].y);
+                        u[4 * j + 2] = __float_as_uint(x[4 * g + j].z); u[4 * j + 3] = __float_as_uint(x[4 * g + j].w);
+                    }
+                    uint4 o[3];
+                    pack24x16(u, o);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) *reinterpret_cast<uint4 *>(&X24[(size_t)((c0 / 16 + g) * 3 + k) * 128]) = o[k];
+                }
             }
             if (ln_out) {   // the new residual as the next GEMM's bf16 operand + this half tile's share of the row statistics
 #pragma unroll
