@@ -1,21 +1,21 @@
 #!/bin/bash
 # evidence pass of the final build: whole GPU suite, smoke, default bench (timed), reference arm, 2M ncu launch list + --set full capture
 cd "$(dirname "$0")/../.."
-O=gpurun_out/r02ag; mkdir -p $O
+O=gpurun_out/r02ap; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q > $O/tests.log 2>&1; echo "tests rc=$?"; tail -4 $O/tests.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
 ( time timeout 900 python bench.py ) > $O/bench_default.json 2> $O/bench_default.err; echo "bench rc=$?"; tail -4 $O/bench_default.err
 ( time timeout 600 python bench.py --impl reference --steps 8 --warmup 3 ) > $O/bench_ref.json 2> $O/bench_ref.err; tail -4 $O/bench_ref.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02b.csv \
-    python bench.py --quick --steps 2 --warmup 1 > gpurun_out/launches_r02b.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02c.csv \
+    python bench.py --quick --steps 2 --warmup 1 > gpurun_out/launches_r02c.log 2>&1
 echo "launch list rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on \
-    -k regex:"post_attn_kernel|attn_persistent|block0_lookup|last_attn" -s 2 -c 6 -f -o gpurun_out/prof_r02b \
-    python bench.py --quick --envs 128 --steps 1 --warmup 1 > gpurun_out/prof_r02b.log 2>&1
+    -k regex:"post_attn_kernel|attn_persistent|block0_lookup|last_attn" -s 2 -c 6 -f -o gpurun_out/prof_r02c \
+    python bench.py --quick --envs 128 --steps 1 --warmup 1 > gpurun_out/prof_r02c.log 2>&1
 echo "full capture (2M) rc=$?"
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r02ag/bench_default.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/r02ap/bench_default.json').read().strip().splitlines()[-1])
 print('value',round(d['value']),'e2e',round(d['e2e']['value']),'frac',d['roofline']['whole_step_frac'], d['roofline']['kernel'], d['roofline']['frac'], d['clocks'], d['gpu_launches'])
 for k,v in d.get('other_configs',{}).items():
     print(k, {kk:(round(vv) if isinstance(vv,float) and vv>100 else vv) for kk,vv in v.items() if kk in ('value','ms_per_step','error')}, v.get('roofline',{}).get('whole_step_frac'), v.get('e2e',{}) and round(v['e2e']['value']))
