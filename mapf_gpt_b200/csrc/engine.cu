@@ -784,11 +784,11 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 pa.timeline = e->d_timeline;
                 if (l == 0 && x_from_tab) { pa.tokens0 = tokens + (size_t)s0 * 256; pa.tab0 = m.tab0; pa.tab_nrec = C / 4 + 3 * C / 8; }
                 // the next block is the pruned last one: it reads the residual and q of token 255 only (last_attn_kernel)
-                static const bool full_tail = getenv("MAPF_GPT_B200_FULL_TAIL_STORES") != nullptr;
+                const bool full_tail = getenv("MAPF_GPT_B200_FULL_TAIL_STORES") != nullptr;   // per forward: tests flip it between engines
                 pa.tail_rows_only = (e->prune_last && l + 2 == m.cfg.n_layer && m.fuse_qkv && !full_tail) ? 1 : 0;
                 // 24-bit residual stream between consecutive post_attn launches (pack24x16); the rows last_attn_kernel / head_kernel
                 // read stay fp32.  MAPF_GPT_B200_X24=0 keeps fp32 everywhere.
-                static const bool x24 = !(getenv("MAPF_GPT_B200_X24") && getenv("MAPF_GPT_B200_X24")[0] == '0');
+                const bool x24 = !(getenv("MAPF_GPT_B200_X24") && getenv("MAPF_GPT_B200_X24")[0] == '0');
                 pa.x_in_24 = (x24 && l > 0) ? 1 : 0;
                 pa.x_out_24 = (x24 && !last && !pa.tail_rows_only && !(e->prune_last && l + 2 == m.cfg.n_layer)) ? 1 : 0;
                 if ((rc = launch_post_attn(e, C, pa, MT, false))) return rc;
@@ -804,7 +804,7 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         bool pruned_tail = false;
         // 24-bit residual stream between the residual GEMMs of the CTA-pair path (GemmArgs::x_in_24 / x_out_24): everything between
         // embed_kernel (writes fp32) and the last full-size residual GEMM (writes fp32 for last_attn_kernel / head_kernel)
-        static const bool x24_env = !(getenv("MAPF_GPT_B200_X24") && getenv("MAPF_GPT_B200_X24")[0] == '0');
+        const bool x24_env = !(getenv("MAPF_GPT_B200_X24") && getenv("MAPF_GPT_B200_X24")[0] == '0');
         const bool x24 = x24_env && lnf;
         const bool tail_pruned = e->prune_last && (hs == 32 || hs == 64) && 32 * H <= 512;
         const int last_full = tail_pruned ? m.cfg.n_layer - 2 : m.cfg.n_layer - 1;   // block whose mlp c_proj is the last full-size one
