@@ -821,6 +821,8 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
             GemmArgs g{};
             g.A = w.XN; g.W = L.wqkv; g.Wp = L.wqkv_p; g.out = w.QKV; g.M = M; g.N = 3 * C; g.K = C; g.C = C; g.n_head = H; g.hs = hs;
             if (lnf) { g.stats_in = w.STATS; g.colsum = L.cs_qkv; }
+            const bool full_tail = getenv("MAPF_GPT_B200_FULL_TAIL_STORES") != nullptr;   // per forward: tests flip it between engines
+            g.tail_rows_only = (tail_pruned && l + 1 == m.cfg.n_layer && !full_tail) ? 1 : 0;   // q of the pruned block: token 255 only
             if ((rc = launch_gemm<EPI_QKV>(e, m.BN, g, KC_QKV))) return rc;
             if (l + 1 == m.cfg.n_layer && e->prune_last && (hs == 32 || hs == 64) && 32 * H <= 512) {
                 // Last block pruned (as on the fused path): only logits[255][0:5] are consumed, so K and V are
@@ -878,6 +880,8 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
                 g.x_in_24 = 1; g.x_out_24 = l < last_full;
                 g.resid_in = w.X24; g.out = l < last_full ? w.X24 : w.X;
             }
+            // last_attn_kernel reads the residual of token 255 only (with a LayerNorm kernel of its own the next block reads every row)
+            g.tail_rows_only = (lnf && tail_pruned && l == last_full && !full_tail) ? 1 : 0;
             if ((rc = launch_gemm<EPI_RESID>(e, m.BN, g, KC_PROJ2))) return rc;
         }
         if (pruned_tail) continue;

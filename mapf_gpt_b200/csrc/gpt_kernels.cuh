@@ -39,6 +39,9 @@ struct GemmArgs {
     // residual INPUT when it is not `out` itself: a launch that changes the layout (fp32 -> 24-bit or back) must not run in
     // place -- the two layouts put different columns at the same address, and other CTAs / threads still read theirs
     const float *resid_in;
+    // pair GEMM only: the consumer of this output is the pruned last block, which reads token 255 of each sequence alone
+    // (last_attn_kernel): EPI_RESID stores the fp32 residual, EPI_QKV the q columns (n < C), for that row only
+    int tail_rows_only;
 };
 
 // erf-GELU (model.py:80, nn.GELU() = x * Phi(x)) on a PAIR of values with packed fp32x2 math.  Three forms, one compiled in.
@@ -309,6 +312,7 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
         const float4 *Xi = reinterpret_cast<const float4 *>(rin) + ((size_t)mt * (a.N / 4) + nbase / 4) * 128 + r;
         const float4 *Xi24 = reinterpret_cast<const float4 *>(rin) + ((size_t)mt * (a.N / 4) + (nbase / 16) * 3) * 128 + r;
         const bool in24 = a.x_in_24 != 0, out24 = a.x_out_24 != 0;
+        const bool keep_row = !a.tail_rows_only || ((mt & 1) && r == 127);
         float4 xa[8], xb[8];
         if (in24) {
 #pragma unroll
@@ -349,7 +353,7 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
                 x[j].y += __uint_as_float(v[4 * j + 1]);
                 x[j].z += __uint_as_float(v[4 * j + 2]);
                 x[j].w += __uint_as_float(v[4 * j + 3]);
-                if (!out24) X[(size_t)(c0 / 4 + j) * 128] = x[j];
+                if (!out24 && keep_row) X[(size_t)(c0 / 4 + j) * 128] = x[j];
             }
             if (out24) {
 #pragma unroll
@@ -451,6 +455,7 @@ __device__ __forceinline__ void pair_epilogue(const GemmArgs &a, int mt, int nt,
             } else {  // EPI_QKV: scatter into [seq][3][head][hs/8][256][8]
                 const int seq = mt >> 1, tok = ((mt & 1) << 7) + r;
                 uint4 *Oseq = reinterpret_cast<uint4 *>(a.out) + (size_t)seq * (3 * a.C / 8) * 256 + tok;
+                if (a.tail_rows_only && n0 < a.C && tok != 255) continue;   // q columns in front of the pruned last block
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     uint4 o;

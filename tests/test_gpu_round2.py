@@ -160,13 +160,13 @@ def test_stream_lanes_rollout_equals_the_single_stream_rollout(built, monkeypatc
     assert (outs[0][0] != st).any()                                       # agents did move
 
 
-@pytest.mark.parametrize("name", ["2M", "6M"])
+@pytest.mark.parametrize("name", ["2M", "6M", "85M"])
 def test_tail_aware_stores_are_bit_identical(built, monkeypatch, name):
     """The launch in front of the pruned last block stores the residual and the q rows of token 255 only (last_attn_kernel reads
     nothing else): logits bit-identical to storing everything (MAPF_GPT_B200_FULL_TAIL_STORES=1)."""
     from mapf_gpt_b200 import engine as E
     cfg, sd = sharp_model(name)
-    toks = np.random.default_rng(11).integers(0, 67, size=(192, 256)).astype(np.int8)
+    toks = np.random.default_rng(11).integers(0, 67, size=(192 if name != "85M" else 128, 256)).astype(np.int8)
     outs = []
     for full in (None, "1"):
         if full:
