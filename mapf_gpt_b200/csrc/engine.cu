@@ -809,6 +809,15 @@ static int forward_device(mg_engine *e, const uint8_t *tokens, int n_seq, float 
         const bool tail_pruned = e->prune_last && (hs == 32 || hs == 64) && 32 * H <= 512;
         const int last_full = tail_pruned ? m.cfg.n_layer - 2 : m.cfg.n_layer - 1;   // block whose mlp c_proj is the last full-size one
         prof_begin(e, KC_EMBED);
+        const bool embed_rows = getenv("MAPF_GPT_B200_EMBED_ROWS") != nullptr;   // A/B and tests: the lane-per-row kernel
+        if (lnf && C == 768 && !embed_rows) {
+            static PerDevice attr_set;
+            if (const int d = cur_device(); !attr_set.v[d].load()) {
+                CU(cudaFuncSetAttribute(embed_tile_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, embed_tile_smem_bytes()));
+                attr_set.v[d].store(1);
+            }
+            embed_tile_kernel<768><<<MT, 128, embed_tile_smem_bytes(), e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, w.XN, w.STATS);
+        } else
         embed_kernel<<<MT, 128, 0, e->stream>>>(tokens + (size_t)s0 * 256, m.wte, m.wpe, w.X, C, lnf ? w.XN : nullptr, w.STATS);
         prof_end(e);
         for (int l = 0; l < m.cfg.n_layer; l++) {

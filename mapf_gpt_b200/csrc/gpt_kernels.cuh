@@ -1469,6 +1469,59 @@ __global__ void __launch_bounds__(128) embed_kernel(const uint8_t *__restrict__ 
     }
 }
 
+// The same outputs as embed_kernel's LayerNorm-folded branch (X_ti, the raw bf16 operand image, the row statistics: bit for bit),
+// without its address-divergent loads: there every lane walks its own wte / wpe row, 32 separate 16-byte requests per load
+// instruction, and the kernel ran at the LSU's request rate (5.8 ms per 8192 sequences at C = 768 = 1.7 TB/s).  Here a warp reads
+// one row at a time with lanes across columns (512 contiguous bytes per instruction), parks a [32 rows][32 column groups] slab in
+// shared memory (pitch 33 groups: conflict-free both ways) and writes it out with lane == row, as the tile layout wants.
+template <int C>
+__global__ void __launch_bounds__(128) embed_tile_kernel(const uint8_t *__restrict__ tokens, const float *__restrict__ wte,
+                                                         const float *__restrict__ wpe, float *__restrict__ X,
+                                                         __nv_bfloat16 *__restrict__ xb_out, float *__restrict__ stats_out)
+{
+    static_assert(C % 128 == 0, "embed_tile_kernel: slabs of 128 columns");
+    extern __shared__ __align__(16) float4 slab_s[];          // [4 warps][32 rows][33]
+    const int mt = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
+    float4 *my = slab_s + warp * 32 * 33;
+    const size_t row = (size_t)mt * 128 + r;
+    const int tok_l = min((int)tokens[row], 66), pos_l = (int)(row & 255);
+    const float4 *wte4 = reinterpret_cast<const float4 *>(wte), *wpe4 = reinterpret_cast<const float4 *>(wpe);
+    float4 *Xo = reinterpret_cast<float4 *>(X) + (size_t)mt * (C / 4) * 128 + r;
+    uint4 *XB = reinterpret_cast<uint4 *>(xb_out) + (size_t)mt * (C / 8) * 128 + r;
+    float s = 0.f, q = 0.f;
+#pragma unroll 1
+    for (int sl = 0; sl < C / 128; sl++) {
+#pragma unroll 8
+        for (int rr = 0; rr < 32; rr++) {
+            const int tok = __shfl_sync(0xffffffffu, tok_l, rr), pos = __shfl_sync(0xffffffffu, pos_l, rr);
+            const float4 t = __ldg(wte4 + (size_t)tok * (C / 4) + sl * 32 + lane), p = __ldg(wpe4 + (size_t)pos * (C / 4) + sl * 32 + lane);
+            my[rr * 33 + lane] = make_float4(t.x + p.x, t.y + p.y, t.z + p.z, t.w + p.w);
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int c = 0; c < 32; c += 2) {
+            const float4 a = my[lane * 33 + c], b = my[lane * 33 + c + 1];
+            Xo[(size_t)(sl * 32 + c) * 128] = a;
+            Xo[(size_t)(sl * 32 + c + 1) * 128] = b;
+            s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+            q += ((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) + ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w));
+            uint4 o;
+            o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+            XB[(size_t)(sl * 16 + c / 2) * 128] = o;
+        }
+        __syncwarp();
+    }
+    constexpr int np = C / 128;
+    float *S = stats_out + ((size_t)mt * np * 2) * 128 + r;
+    S[0] = s;
+    S[128] = q;
+    for (int p = 1; p < np; p++) {
+        S[(size_t)(2 * p) * 128] = 0.f;
+        S[(size_t)(2 * p + 1) * 128] = 0.f;
+    }
+}
+constexpr int embed_tile_smem_bytes() { return 4 * 32 * 33 * 16; }
+
 // LayerNorm, eps 1e-5, gain only (model.py:11-20): X_ti fp32 -> A_ti bf16
 __global__ void __launch_bounds__(128) ln_kernel(const float *__restrict__ X, const float *__restrict__ gain,
                                                  __nv_bfloat16 *__restrict__ out, int C)

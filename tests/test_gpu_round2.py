@@ -203,6 +203,23 @@ def test_24bit_residual_stream_vs_fp32_residual(built, monkeypatch, name, rows):
     assert float(np.abs(outs[0] - outs[1]).max()) < 1e-2
 
 
+def test_embed_tile_kernel_equals_the_row_kernel(built, monkeypatch):
+    """85M path: embed_tile_kernel (warp per row, slab transposed through shared memory) writes what embed_kernel writes
+    (residual, raw bf16 operand image, row statistics): logits bit-identical."""
+    from mapf_gpt_b200 import engine as E
+    cfg, sd = sharp_model("85M", 1.0)
+    toks = np.random.default_rng(5).integers(0, 67, size=(130, 256)).astype(np.int8)
+    outs = []
+    for rows in (None, "1"):
+        if rows:
+            monkeypatch.setenv("MAPF_GPT_B200_EMBED_ROWS", rows)
+        eng = E.RolloutEngine(1, 4, 16, 16)
+        eng.load_model(sd, cfg)
+        outs.append(eng.forward_tokens(toks))
+        eng.close()
+    assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
+
+
 # ------------------------------------------------------------------------------------------------ full-size parity
 @pytest.mark.parametrize("name,n,envs,model", [("wfi_warehouse", 192, 512, "6M"), ("Berlin_1_256_05", 256, 32, "85M"),
                                                ("validation-mazes-seed-000", 256, 256, "2M")])
